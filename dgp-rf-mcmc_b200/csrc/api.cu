@@ -1,0 +1,416 @@
+// C ABI of libdgprf (see include/dgprf.h): argument validation, workspace layout and the
+// per-layer launch sequences.  No state is kept between calls; nothing is allocated.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "kernels.cuh"
+
+static thread_local char g_err[512] = "";
+
+void dgprf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* dgprf_last_error(void) { return g_err; }
+extern "C" int dgprf_version(void) { return 100; }
+
+// ---- workspace layout ------------------------------------------------------------------------
+struct LayerWs {
+    int CS;
+    int64_t n_phi, n_fpart, n_dpart, n_tpart, n_rpart;       // floats per chain
+    size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
+};
+struct WsLayout {
+    LayerWs L[DGPRF_MAX_LAYERS];
+    int RS;
+    int64_t w_len, h_len, n_dflast;
+    size_t dflast, gwpart, ghyp, llsum, total;
+};
+
+static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
+static inline int layer_d(const dgprf_layer& l) { return l.d_prev + l.d_x; }
+
+static int validate_model(const dgprf_model* m) {
+    DGPRF_REQUIRE(m != nullptr, "model is NULL");
+    DGPRF_REQUIRE(m->n_layers >= 1 && m->n_layers <= DGPRF_MAX_LAYERS, "n_layers=%d out of [1,%d]", m->n_layers, DGPRF_MAX_LAYERS);
+    DGPRF_REQUIRE(m->n_chains >= 1, "n_chains=%d", m->n_chains);
+    DGPRF_REQUIRE(m->likelihood == DGPRF_LIK_GAUSSIAN || m->likelihood == DGPRF_LIK_SOFTMAX, "unknown likelihood %d", m->likelihood);
+    DGPRF_REQUIRE(m->precision == DGPRF_PREC_FP32 || m->precision == DGPRF_PREC_TF32, "unknown precision %d", m->precision);
+    DGPRF_REQUIRE(m->w_base && m->h_base, "parameter buffers are NULL");
+    DGPRF_REQUIRE(m->likelihood != DGPRF_LIK_GAUSSIAN || m->off_lik_log_var >= 0, "Gaussian likelihood needs lik_log_var");
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        DGPRF_REQUIRE(y.kind == DGPRF_KIND_RBF || y.kind == DGPRF_KIND_ARC, "layer %d: unknown kind %d", l, y.kind);
+        DGPRF_REQUIRE(y.M >= 1 && y.g >= 1 && y.g <= 64, "layer %d: M=%d g=%d unsupported (need M>=1, 1<=g<=64)", l, y.M, y.g);
+        DGPRF_REQUIRE(y.d_prev >= 0 && y.d_x >= 0 && layer_d(y) >= 1 && layer_d(y) <= 8192, "layer %d: input width %d unsupported", l, layer_d(y));
+        DGPRF_REQUIRE(y.d_x <= m->d_in, "layer %d: d_x=%d > d_in=%d", l, y.d_x, m->d_in);
+        DGPRF_REQUIRE(l == 0 ? y.d_prev == 0 : y.d_prev == m->layer[l - 1].g, "layer %d: d_prev=%d does not chain", l, y.d_prev);
+        DGPRF_REQUIRE(y.z != nullptr, "layer %d: z is NULL", l);
+        DGPRF_REQUIRE(y.off_W >= 0 && (y.off_W & 3) == 0, "layer %d: off_W must be a non-negative multiple of 4", l);
+    }
+    DGPRF_REQUIRE(m->layer[m->n_layers - 1].g == m->d_out, "last n_gp=%d != d_out=%d", m->layer[m->n_layers - 1].g, m->d_out);
+    return DGPRF_OK;
+}
+
+static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
+    DGPRF_REQUIRE(B >= 1, "B=%d", B);
+    DGPRF_REQUIRE(mode >= DGPRF_MODE_EVAL && mode <= DGPRF_MODE_HYPER, "unknown mode %d", mode);
+    memset(w, 0, sizeof(*w));
+    const int64_t C = m->n_chains;
+    size_t off = 0;
+    auto take = [&](int64_t floats_per_chain) {
+        const size_t at = off;
+        off += (size_t)round_up(floats_per_chain * C * (int64_t)sizeof(float), 256);
+        return at;
+    };
+    w->RS = row_splits(B);
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        LayerWs& s = w->L[l];
+        s.CS = col_splits(y.M);
+        s.n_fpart = (int64_t)s.CS * B * y.g;
+        s.fpart = take(s.n_fpart);
+        if (mode >= DGPRF_MODE_TRAIN) {
+            s.n_phi = (int64_t)B * layer_F(y);
+            s.phi = take(s.n_phi);
+            if (l > 0) { s.n_dpart = (int64_t)s.CS * B * y.d_prev; s.dpart = take(s.n_dpart); }
+        }
+        if (mode == DGPRF_MODE_HYPER) {
+            s.n_tpart = (int64_t)s.CS * B * layer_d(y); s.tpart = take(s.n_tpart);
+            s.n_rpart = (int64_t)s.CS * B;              s.rpart = take(s.n_rpart);
+        }
+        const int64_t wend = y.off_W + (int64_t)layer_F(y) * y.g;
+        if (wend > w->w_len) w->w_len = wend;
+        int64_t hend = y.off_log_amp + 1;
+        if (y.off_log_inv_ls + layer_d(y) > hend) hend = y.off_log_inv_ls + layer_d(y);
+        if (y.has_mean && y.off_mean + layer_d(y) > hend) hend = y.off_mean + layer_d(y);
+        if (hend > w->h_len) w->h_len = hend;
+    }
+    if (m->off_lik_log_var + 1 > w->h_len) w->h_len = m->off_lik_log_var + 1;
+    w->w_len = round_up(w->w_len, 4);
+    w->h_len = round_up(w->h_len, 4);
+    w->llsum = take(1);
+    if (mode >= DGPRF_MODE_TRAIN) {
+        w->n_dflast = (int64_t)B * m->d_out;
+        w->dflast = take(w->n_dflast);
+        w->gwpart = take((int64_t)w->RS * w->w_len);
+    }
+    if (mode == DGPRF_MODE_HYPER) w->ghyp = take(w->h_len);
+    w->total = off;
+    return DGPRF_OK;
+}
+
+static inline float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(ws) + off); }
+
+static int check_ws(const dgprf_model* m, int B, int mode, void* ws, size_t ws_bytes, WsLayout* w) {
+    int rc = validate_model(m);
+    if (rc) return rc;
+    rc = make_layout(m, B, mode, w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(ws != nullptr, "workspace is NULL");
+    DGPRF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    if (ws_bytes < w->total) {
+        dgprf_set_error("workspace too small: %zu < %zu bytes", ws_bytes, w->total);
+        return DGPRF_EWORKSPACE;
+    }
+    return DGPRF_OK;
+}
+
+extern "C" int dgprf_workspace_bytes(const dgprf_model* m, int B, int mode, size_t* bytes) {
+    DGPRF_REQUIRE(bytes != nullptr, "bytes is NULL");
+    int rc = validate_model(m);
+    if (rc) return rc;
+    WsLayout w;
+    rc = make_layout(m, B, mode, &w);
+    if (rc) return rc;
+    *bytes = w.total;
+    return DGPRF_OK;
+}
+
+static SlabMat fpart_of(const dgprf_model* m, const WsLayout& w, void* ws, int l, int B) {
+    SlabMat s;
+    s.ptr = wsf(ws, w.L[l].fpart);
+    s.cs = w.L[l].n_fpart;
+    s.ss = (int64_t)B * m->layer[l].g;
+    s.ld = m->layer[l].g;
+    s.n_slabs = w.L[l].CS;
+    return s;
+}
+
+// ---- forward -----------------------------------------------------------------------------------
+static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X, int64_t x_cs, int B, int mode,
+                        void* ws, float* F_out, cudaStream_t st) {
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        FwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.kind = y.kind; a.B = B; a.d_prev = y.d_prev; a.d_x = y.d_x; a.d = layer_d(y);
+        a.M = y.M; a.g = y.g; a.F = layer_F(y); a.CS = w.L[l].CS; a.ldx = m->d_in; a.do_gemm2 = 1;
+        a.has_mean = y.has_mean;
+        if (l > 0) a.Fprev = fpart_of(m, w, ws, l - 1, B);
+        a.X = X; a.x_cs = x_cs;
+        a.z = y.z; a.z_cs = y.z_cs;
+        a.log_inv_ls = m->h_base + y.off_log_inv_ls;
+        a.log_amp = m->h_base + y.off_log_amp;
+        a.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
+        a.h_cs = m->h_cs;
+        a.W = m->w_base + y.off_W; a.w_cs = m->w_cs;
+        a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
+        a.phi_cs = w.L[l].n_phi;
+        a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
+        const int rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
+        if (rc) return rc;
+    }
+    if (F_out) {
+        const int L = m->n_layers - 1;
+        return dgprf_launch_sum_slabs(fpart_of(m, w, ws, L, B), B, m->d_out, F_out, (int64_t)B * m->d_out, m->n_chains, st);
+    }
+    return DGPRF_OK;
+}
+
+extern "C" int dgprf_forward(const dgprf_model* m, const float* X, int64_t x_cs, int B, int mode,
+                             void* ws, size_t ws_bytes, float* F_out, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(X != nullptr, "X is NULL");
+    return forward_impl(m, w, X, x_cs, B, mode, ws, F_out, (cudaStream_t)stream);
+}
+
+// ---- likelihood ----------------------------------------------------------------------------------
+static int loglik_impl(const dgprf_model* m, const WsLayout& w, const float* Y, int64_t y_cs, int B, int mode,
+                       void* ws, float* ll_rows, float* aux_rows, float* ll_sum, float inv_B, cudaStream_t st) {
+    const int L = m->n_layers - 1;
+    LikArgs a;
+    memset(&a, 0, sizeof(a));
+    a.likelihood = m->likelihood; a.B = B; a.D = m->d_out;
+    a.F = fpart_of(m, w, ws, L, B);
+    a.Y = Y; a.y_cs = y_cs;
+    a.lik_log_var = m->likelihood == DGPRF_LIK_GAUSSIAN ? m->h_base + m->off_lik_log_var : nullptr;
+    a.h_cs = m->h_cs;
+    a.ll_rows = ll_rows; a.aux_rows = aux_rows;
+    a.ll_sum = ll_sum ? ll_sum : wsf(ws, w.llsum);
+    a.inv_B = inv_B;
+    if (inv_B > 0.f) {
+        DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "dU/dF needs a TRAIN/HYPER workspace");
+        a.dF = wsf(ws, w.dflast); a.df_cs = w.n_dflast;
+        if (mode == DGPRF_MODE_HYPER) {
+            DGPRF_CHECK_CUDA(cudaMemsetAsync(wsf(ws, w.ghyp), 0, sizeof(float) * w.h_len * m->n_chains, st));
+            if (m->likelihood == DGPRF_LIK_GAUSSIAN) {
+                a.g_lik_log_var = wsf(ws, w.ghyp) + m->off_lik_log_var;
+                a.g_cs = w.h_len;
+            }
+        }
+    }
+    return dgprf_launch_loglik(a, m->n_chains, st);
+}
+
+extern "C" int dgprf_loglik(const dgprf_model* m, const float* Y, int64_t y_cs, int B, int mode,
+                            void* ws, size_t ws_bytes, float* ll_rows, float* aux_rows, float* ll_sum,
+                            float inv_B, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(Y != nullptr, "Y is NULL");
+    return loglik_impl(m, w, Y, y_cs, B, mode, ws, ll_rows, aux_rows, ll_sum, inv_B, (cudaStream_t)stream);
+}
+
+// ---- backward -------------------------------------------------------------------------------------
+static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X, int64_t x_cs, int B, int mode,
+                         void* ws, cudaStream_t st) {
+    const int hyper = mode == DGPRF_MODE_HYPER;
+    for (int l = m->n_layers - 1; l >= 0; --l) {
+        const dgprf_layer& y = m->layer[l];
+        BwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.kind = y.kind; a.B = B; a.d_prev = y.d_prev; a.d_x = y.d_x; a.d = layer_d(y);
+        a.M = y.M; a.g = y.g; a.F = layer_F(y); a.CS = w.L[l].CS; a.RS = w.RS; a.ldx = m->d_in;
+        a.has_mean = y.has_mean; a.hyper = hyper;
+        if (l == m->n_layers - 1) {
+            a.dF.ptr = wsf(ws, w.dflast); a.dF.cs = w.n_dflast; a.dF.ss = 0; a.dF.ld = y.g; a.dF.n_slabs = 1;
+        } else {
+            a.dF.ptr = wsf(ws, w.L[l + 1].dpart); a.dF.cs = w.L[l + 1].n_dpart;
+            a.dF.ss = (int64_t)B * y.g; a.dF.ld = y.g; a.dF.n_slabs = w.L[l + 1].CS;
+        }
+        a.Phi = wsf(ws, w.L[l].phi); a.phi_cs = w.L[l].n_phi;
+        a.z = y.z; a.z_cs = y.z_cs;
+        a.log_inv_ls = m->h_base + y.off_log_inv_ls;
+        a.log_amp = m->h_base + y.off_log_amp;
+        a.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
+        a.h_cs = m->h_cs;
+        a.W = m->w_base + y.off_W; a.w_cs = m->w_cs;
+        a.gWpart = wsf(ws, w.gwpart) + y.off_W; a.gw_cs = (int64_t)w.RS * w.w_len; a.gw_ss = w.w_len;
+        a.Dpart = l > 0 ? wsf(ws, w.L[l].dpart) : nullptr; a.d_cs = w.L[l].n_dpart;
+        a.Tpart = hyper ? wsf(ws, w.L[l].tpart) : nullptr; a.t_cs = w.L[l].n_tpart;
+        a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
+        int rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
+        if (rc) return rc;
+        if (hyper) {
+            HypArgs h;
+            memset(&h, 0, sizeof(h));
+            h.B = B; h.d = a.d; h.d_prev = y.d_prev; h.d_x = y.d_x; h.g = y.g; h.ldx = m->d_in; h.has_mean = y.has_mean;
+            if (l > 0) h.Fprev = fpart_of(m, w, ws, l - 1, B);
+            h.X = X; h.x_cs = x_cs;
+            h.T.ptr = a.Tpart; h.T.cs = a.t_cs; h.T.ss = (int64_t)B * a.d; h.T.ld = a.d; h.T.n_slabs = a.CS;
+            h.R.ptr = a.Rpart; h.R.cs = a.r_cs; h.R.ss = B; h.R.ld = 1; h.R.n_slabs = a.CS;
+            h.dF = a.dF;
+            h.Fcur = fpart_of(m, w, ws, l, B);
+            h.log_inv_ls = a.log_inv_ls; h.h_cs = m->h_cs;
+            h.gH = wsf(ws, w.ghyp); h.gh_cs = w.h_len;
+            h.off_log_amp = y.off_log_amp; h.off_log_inv_ls = y.off_log_inv_ls; h.off_mean = y.off_mean;
+            rc = dgprf_launch_hyper_reduce(h, m->n_chains, st);
+            if (rc) return rc;
+        }
+    }
+    return DGPRF_OK;
+}
+
+extern "C" int dgprf_backward(const dgprf_model* m, const float* X, int64_t x_cs, int B, int mode,
+                              void* ws, size_t ws_bytes, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "backward needs a TRAIN/HYPER workspace");
+    DGPRF_REQUIRE(X != nullptr, "X is NULL");
+    return backward_impl(m, w, X, x_cs, B, mode, ws, (cudaStream_t)stream);
+}
+
+extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* ws, size_t ws_bytes,
+                                   float* gW, int64_t gw_cs, float* gH, int64_t gh_cs,
+                                   float prior_inv_N, int prior_hyper, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "grad_finalize needs a TRAIN/HYPER workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gW) {
+        DGPRF_REQUIRE(gw_cs >= w.w_len, "gW chain stride %lld < %lld", (long long)gw_cs, (long long)w.w_len);
+        rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), (int64_t)w.RS * w.w_len, w.w_len, w.RS,
+                                        m->w_base, m->w_cs, prior_inv_N, gW, gw_cs, w.w_len, m->n_chains, st);
+        if (rc) return rc;
+    }
+    if (gH) {
+        DGPRF_REQUIRE(mode == DGPRF_MODE_HYPER, "hyper gradients need a HYPER workspace");
+        DGPRF_REQUIRE(gh_cs >= w.h_len, "gH chain stride %lld < %lld", (long long)gh_cs, (long long)w.h_len);
+        rc = dgprf_launch_grad_finalize(wsf(ws, w.ghyp), w.h_len, 0, 1, m->h_base, m->h_cs,
+                                        prior_hyper ? prior_inv_N : 0.f, gH, gh_cs, w.h_len, m->n_chains, st);
+        if (rc) return rc;
+    }
+    return DGPRF_OK;
+}
+
+// ---- update -----------------------------------------------------------------------------------------
+static int update_impl(float* theta, float* mom, int64_t cs, int64_t n, int n_chains,
+                       const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
+                       const dgprf_segment* segs, int n_seg, float lr, float data_size, float beta,
+                       float temperature, int resample, uint64_t seed, uint64_t step, uint32_t stream_base,
+                       const float* eps_inject, const float* mom_inject, cudaStream_t st) {
+    DGPRF_REQUIRE(theta && mom && grad && segs, "update: NULL buffer");
+    DGPRF_REQUIRE(lr > 0.f && data_size > 0.f && beta >= 0.f && beta < 1.f && temperature >= 0.f,
+                  "update: need lr>0, N>0, 0<=beta<1, T>=0");
+    UpdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.theta = theta; a.mom = mom; a.cs = cs; a.n = n;
+    a.grad = grad; a.grad_cs = grad_cs; a.n_part = n_part; a.part_stride = part_stride; a.n_seg = n_seg;
+    a.h = sqrtf(lr / data_size); a.hN = a.h * data_size; a.beta = beta;
+    a.noise_scale = sqrtf(2.f * (1.f - beta) * temperature);
+    a.inv_N = 1.f / data_size;
+    a.resample = resample; a.seed = seed; a.step = step; a.stream_base = stream_base;
+    a.eps_inject = eps_inject; a.mom_inject = mom_inject;
+    return dgprf_launch_update(a, segs, n_seg, n_chains, st);
+}
+
+extern "C" int dgprf_sgmcmc_update(float* theta, float* mom, int64_t cs, int64_t n, int n_chains,
+                                   const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
+                                   const dgprf_segment* segs, int n_seg,
+                                   float lr, float data_size, float momentum_decay, float temperature,
+                                   int resample_moments, uint64_t seed, uint64_t step,
+                                   const float* eps_inject, const float* mom_inject, void* stream) {
+    DGPRF_REQUIRE(n_part >= 1 && n_chains >= 1, "update: n_part/n_chains must be >= 1");
+    return update_impl(theta, mom, cs, n, n_chains, grad, grad_cs, n_part, part_stride, segs, n_seg, lr, data_size,
+                       momentum_decay, temperature, resample_moments, seed, step, 0u, eps_inject, mom_inject,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y,
+                                 int64_t y_cs, int B, int full_bayesian,
+                                 float* theta_w, float* mom_w, int64_t w_len,
+                                 const dgprf_segment* segs_w, int n_seg_w,
+                                 float* theta_h, float* mom_h, int64_t h_len,
+                                 const dgprf_segment* segs_h, int n_seg_h,
+                                 float lr, float data_size, float momentum_decay, float temperature,
+                                 int resample_moments, uint64_t seed, uint64_t step,
+                                 const float* eps_w, const float* res_w, const float* eps_h, const float* res_h,
+                                 void* ws, size_t ws_bytes, float* u_out, void* stream) {
+    const int mode = full_bayesian ? DGPRF_MODE_HYPER : DGPRF_MODE_TRAIN;
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(X && Y, "X/Y is NULL");
+    DGPRF_REQUIRE(theta_w == m->w_base, "theta_w must alias model.w_base");
+    DGPRF_REQUIRE(w_len == w.w_len, "w_len=%lld, layout expects %lld", (long long)w_len, (long long)w.w_len);
+    DGPRF_REQUIRE(m->w_cs >= w_len || m->n_chains == 1, "w chain stride too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = forward_impl(m, w, X, x_cs, B, mode, ws, nullptr, st);
+    if (rc) return rc;
+    rc = loglik_impl(m, w, Y, y_cs, B, mode, ws, nullptr, nullptr, u_out, 1.f / (float)B, st);
+    if (rc) return rc;
+    rc = backward_impl(m, w, X, x_cs, B, mode, ws, st);
+    if (rc) return rc;
+    rc = update_impl(theta_w, mom_w, m->w_cs, w_len, m->n_chains, wsf(ws, w.gwpart), (int64_t)w.RS * w.w_len, w.RS,
+                     w.w_len, segs_w, n_seg_w, lr, data_size, momentum_decay, temperature, resample_moments, seed,
+                     step, 0u, eps_w, res_w, st);
+    if (rc) return rc;
+    if (full_bayesian && n_seg_h > 0) {
+        DGPRF_REQUIRE(theta_h == m->h_base, "theta_h must alias model.h_base");
+        DGPRF_REQUIRE(h_len == w.h_len, "h_len=%lld, layout expects %lld", (long long)h_len, (long long)w.h_len);
+        rc = update_impl(theta_h, mom_h, m->h_cs, h_len, m->n_chains, wsf(ws, w.ghyp), w.h_len, 1, 0, segs_h,
+                         n_seg_h, lr, data_size, momentum_decay, temperature, resample_moments, seed, step, 2u,
+                         eps_h, res_h, st);
+        if (rc) return rc;
+    }
+    return DGPRF_OK;
+}
+
+// ---- stand-alone layer ops -----------------------------------------------------------------------------
+extern "C" int dgprf_rf_features(int kind, const float* X, int B, int d, const float* z, const float* log_inv_ls,
+                                 const float* log_amp, const float* mean, int M, float* Phi, void* stream) {
+    DGPRF_REQUIRE(kind == DGPRF_KIND_RBF || kind == DGPRF_KIND_ARC, "unknown kind %d", kind);
+    DGPRF_REQUIRE(X && z && log_inv_ls && log_amp && Phi && B >= 0 && d >= 1 && M >= 1, "rf_features: bad arguments");
+    if (B == 0) return DGPRF_OK;
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kind = kind; a.B = B; a.d_prev = 0; a.d_x = d; a.d = d; a.M = M; a.g = 1;
+    a.F = kind == DGPRF_KIND_RBF ? 2 * M : M; a.CS = col_splits(M); a.ldx = d; a.do_gemm2 = 0;
+    a.has_mean = mean != nullptr;
+    a.X = X; a.z = z; a.log_inv_ls = log_inv_ls; a.log_amp = log_amp; a.mean = mean;
+    a.W = nullptr; a.Phi = Phi;
+    return dgprf_launch_fwd_simt(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" int dgprf_gaussian_log_prob(const float* F, const float* Y, const float* lik_log_var, int B, int D,
+                                       float* out_rows, void* stream) {
+    DGPRF_REQUIRE(F && Y && lik_log_var && out_rows && B >= 0 && D >= 1, "gaussian_log_prob: bad arguments");
+    if (B == 0) return DGPRF_OK;
+    LikArgs a;
+    memset(&a, 0, sizeof(a));
+    a.likelihood = DGPRF_LIK_GAUSSIAN; a.B = B; a.D = D;
+    a.F.ptr = F; a.F.ld = D; a.F.n_slabs = 1;
+    a.Y = Y; a.lik_log_var = lik_log_var; a.ll_rows = out_rows;
+    return dgprf_launch_loglik(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" int dgprf_softmax_log_prob(const float* F, const float* Y, int B, int C, float* out_rows,
+                                      float* probs, void* stream) {
+    DGPRF_REQUIRE(F && (Y || !out_rows) && B >= 0 && C >= 1, "softmax_log_prob: bad arguments");
+    if (B == 0) return DGPRF_OK;
+    LikArgs a;
+    memset(&a, 0, sizeof(a));
+    a.likelihood = DGPRF_LIK_SOFTMAX; a.B = B; a.D = C;
+    a.F.ptr = F; a.F.ld = C; a.F.n_slabs = 1;
+    a.Y = Y; a.ll_rows = out_rows; a.probs = probs;
+    return dgprf_launch_loglik(a, 1, (cudaStream_t)stream);
+}

@@ -1,0 +1,115 @@
+// Shared device helpers and kernel-argument structs for libdgprf (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/dgprf.h"
+
+#define DGPRF_LOG_2PI 1.8378770664093453f
+
+// ---- error plumbing (api.cu owns the thread-local message) -------------------------------
+void dgprf_set_error(const char* fmt, ...);
+#define DGPRF_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            dgprf_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DGPRF_ECUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+#define DGPRF_REQUIRE(cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            dgprf_set_error(__VA_ARGS__);                                                   \
+            return DGPRF_EINVAL;                                                            \
+        }                                                                                   \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }
+
+// ---- tile geometry of the SIMT (fp32) layer kernels ---------------------------------------
+constexpr int kTM = 64;        // batch rows per tile
+constexpr int kTN = 64;        // random-feature columns per tile
+constexpr int kKC = 32;        // K chunk of GEMM #1 (input width)
+constexpr int kMaxCS = 8;      // column splits  -> partial slabs of F / dF_prev
+constexpr int kMaxRS = 16;     // row splits     -> partial slabs of gW
+constexpr int kThreads = 256;
+
+static inline int col_splits(int M) { int t = ceil_div(M, kTN); return t < kMaxCS ? t : kMaxCS; }
+static inline int row_splits(int B) { int t = ceil_div(B, kTM); return t < kMaxRS ? t : kMaxRS; }
+static inline int pad_g(int g) { return g <= 4 ? 4 : g <= 16 ? 16 : g <= 32 ? 32 : g <= 64 ? 64 : -1; }
+
+// A matrix given as a sum of `n_slabs` partial slabs: value(c,row,col) =
+// sum_s ptr[c*cs + s*ss + row*ld + col].  n_slabs==1 is a plain dense matrix.
+struct SlabMat {
+    const float* ptr;
+    int64_t cs;      // chain stride
+    int64_t ss;      // slab stride
+    int32_t ld;      // leading dimension
+    int32_t n_slabs;
+};
+
+__device__ __forceinline__ float slab_load(const SlabMat& m, int chain, int64_t row, int col) {
+    const float* p = m.ptr + chain * m.cs + row * m.ld + col;
+    float v = 0.f;
+    for (int s = 0; s < m.n_slabs; ++s) v += __ldg(p + s * m.ss);
+    return v;
+}
+
+struct FwdArgs {
+    int32_t kind, B, d_prev, d_x, d, M, g, F, CS, ldx, do_gemm2, has_mean;
+    SlabMat Fprev;                       // previous GP-layer output (partial slabs), ld = d_prev
+    const float* X;  int64_t x_cs;       // model input, ld = ldx
+    const float* z;  int64_t z_cs;       // [d, M]
+    const float* log_inv_ls; const float* log_amp; const float* mean; int64_t h_cs;
+    const float* W;  int64_t w_cs;       // [F, g]
+    float* Phi;      int64_t phi_cs;     // [B, F] nullable
+    float* Fpart;    int64_t fpart_cs;   // [CS][B][g]
+};
+
+struct BwdArgs {
+    int32_t kind, B, d_prev, d_x, d, M, g, F, CS, RS, ldx, has_mean, hyper;
+    SlabMat dF;                          // dU/dF_l  (ld = g)
+    const float* Phi; int64_t phi_cs;    // saved features [B, F]
+    const float* z;   int64_t z_cs;
+    const float* log_inv_ls; const float* log_amp; const float* mean; int64_t h_cs;
+    const float* W;   int64_t w_cs;
+    float* gWpart;    int64_t gw_cs, gw_ss;   // [RS][w_len] already offset by off_W
+    float* Dpart;     int64_t d_cs;           // [CS][B][d_prev]  dU/dF_{l-1} partials (nullable)
+    float* Tpart;     int64_t t_cs;           // [CS][B][d]       raw T = dP z^T     (hyper)
+    float* Rpart;     int64_t r_cs;           // [CS][B]          R = rowsum(dP)     (hyper | mean)
+};
+
+// ---- device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` needs >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = lane < nw ? red[lane] : 0.f;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// sin/cos with a 2-constant Cody-Waite reduction to [-pi, pi] followed by the MUFU
+// approximations (abs error ~5e-7 on the reduced range).  Random-feature phases reach
+// |P| >> pi, where bare __sinf/__cosf lose all accuracy.
+__device__ __forceinline__ void sincos_cw(float x, float* s, float* c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);        // 2*pi rounded to fp32
+    r = fmaf(-k, -1.7484555e-7f, r);                   // 2*pi - fp32(2*pi)
+    *s = __sinf(r);
+    *c = __cosf(r);
+}

@@ -1,0 +1,249 @@
+// Small kernels around the hot path: slab sums, gradient finalisation, hyper-parameter
+// gradient reduction (K8 tail), log-prior (K4), Adam, Welford/mass (K6), stand-alone GP matmul.
+#include "common.cuh"
+#include "philox.cuh"
+#include "kernels.cuh"
+
+// ---- dense = sum of slabs ------------------------------------------------------------------
+__global__ void k_sum_slabs(SlabMat m, int B, int ncol, float* out, int64_t out_cs) {
+    const int chain = blockIdx.y;
+    const int64_t n = (int64_t)B * ncol;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        out[chain * out_cs + e] = slab_load(m, chain, e / ncol, (int)(e % ncol));
+}
+
+int dgprf_launch_sum_slabs(const SlabMat& m, int B, int ncol, float* out, int64_t out_cs, int n_chains, cudaStream_t st) {
+    int blocks = ceil_div((int64_t)B * ncol, 256);
+    if (blocks > 1184) blocks = 1184;
+    k_sum_slabs<<<dim3(blocks, n_chains), 256, 0, st>>>(m, B, ncol, out, out_cs);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- gradient finalisation: out = sum_p part_p (+ theta * inv_N) ---------------------------
+__global__ void k_grad_finalize(const float* part, int64_t part_cs, int64_t part_ss, int n_part,
+                                const float* theta, int64_t theta_cs, float inv_N,
+                                float* out, int64_t out_cs, int64_t n) {
+    const int chain = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float g = 0.f;
+        for (int p = 0; p < n_part; ++p) g += __ldg(part + chain * part_cs + p * part_ss + i);
+        if (inv_N != 0.f) g = fmaf(__ldg(theta + chain * theta_cs + i), inv_N, g);
+        out[chain * out_cs + i] = g;
+    }
+}
+
+int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_ss, int n_part,
+                               const float* theta, int64_t theta_cs, float inv_N,
+                               float* out, int64_t out_cs, int64_t n, int n_chains, cudaStream_t st) {
+    int blocks = ceil_div(n, 256);
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    k_grad_finalize<<<dim3(blocks, n_chains), 256, 0, st>>>(part, part_cs, part_ss, n_part, theta, theta_cs,
+                                                            inv_N, out, out_cs, n);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- K8 tail: hyper-parameter gradients of one layer from T, R, dF, F ----------------------
+//   d log_inv_ls[q] = exp(log_inv_ls[q]) * sum_i in[i,q] * T[i,q]
+//   d mean[q]       = sum_i in[i,q] * R[i]
+//   d log_amp       = sum_ij dF[i,j] * F[i,j]
+// grid (ceil(d/32)+1, C): the last block of each chain does log_amp.
+__global__ void __launch_bounds__(256) k_hyper_reduce(const HypArgs a) {
+    __shared__ float red_a[8][33];
+    __shared__ float red_b[8][33];
+    __shared__ float red[32];
+    const int chain = blockIdx.y;
+    const int nqb = (a.d + 31) / 32;
+    float* gH = a.gH + chain * a.gh_cs;
+    if ((int)blockIdx.x == nqb) {
+        float acc = 0.f;
+        const int64_t n = (int64_t)a.B * a.g;
+        for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const int64_t row = e / a.g; const int j = (int)(e % a.g);
+            acc += slab_load(a.dF, chain, row, j) * slab_load(a.Fcur, chain, row, j);
+        }
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) gH[a.off_log_amp] = acc;
+        return;
+    }
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
+    float acc_ls = 0.f, acc_mu = 0.f;
+    if (q < a.d) {
+        const float* X = a.X + chain * a.x_cs;
+        for (int64_t row = rg; row < a.B; row += 8) {
+            const float in = q < a.d_prev ? slab_load(a.Fprev, chain, row, q)
+                                          : __ldg(X + row * a.ldx + (q - a.d_prev));
+            acc_ls = fmaf(in, slab_load(a.T, chain, row, q), acc_ls);
+            if (a.has_mean) acc_mu = fmaf(in, slab_load(a.R, chain, row, 0), acc_mu);
+        }
+    }
+    red_a[rg][lane] = acc_ls;
+    red_b[rg][lane] = acc_mu;
+    __syncthreads();
+    if (rg == 0 && q < a.d) {
+        float s = 0.f, m = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { s += red_a[r][lane]; m += red_b[r][lane]; }
+        const float sq = expf(__ldg(a.log_inv_ls + chain * a.h_cs + q));
+        gH[a.off_log_inv_ls + q] = sq * s;
+        if (a.has_mean) gH[a.off_mean + q] = m;
+    }
+}
+
+int dgprf_launch_hyper_reduce(const HypArgs& a, int n_chains, cudaStream_t st) {
+    dim3 grid((a.d + 31) / 32 + 1, n_chains);
+    k_hyper_reduce<<<grid, 256, 0, st>>>(a);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- K4: sum log N(x;0,1) -------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k4_log_prior(const float* x, int64_t cs, int64_t n, float* out) {
+    __shared__ float red[32];
+    const int chain = blockIdx.x;
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = __ldg(x + chain * cs + i);
+        acc = fmaf(v, v, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[chain] = -0.5f * ((float)n * DGPRF_LOG_2PI + acc);
+}
+
+extern "C" int dgprf_log_prior(const float* x, int64_t cs, int64_t n, int n_chains, float* out, void* stream) {
+    DGPRF_REQUIRE(x && out && n >= 0 && n_chains >= 1, "log_prior: bad arguments");
+    k4_log_prior<<<n_chains, 1024, 0, (cudaStream_t)stream>>>(x, cs, n, out);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- Adam (keras semantics: lr_t = lr sqrt(1-b2^t)/(1-b1^t); theta -= lr_t m/(sqrt(v)+eps)) --
+__global__ void k_adam(float* theta, const float* grad, float* m, float* v, int64_t n,
+                       float lr_t, float b1, float b2, float eps) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi; v[i] = vi;
+        theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+extern "C" int dgprf_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n,
+                               float lr, float beta1, float beta2, float eps, int t, void* stream) {
+    DGPRF_REQUIRE(theta && grad && m && v && n >= 0 && t >= 1, "adam_step: bad arguments");
+    if (n == 0) return DGPRF_OK;
+    const float lr_t = lr * sqrtf(1.f - powf(beta2, (float)t)) / (1.f - powf(beta1, (float)t));
+    int blocks = ceil_div(n, 256); if (blocks > 1184) blocks = 1184;
+    k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, lr_t, beta1, beta2, eps);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- K6: Welford update and per-tensor mass (models/dgp.py:259-288) -------------------------
+__global__ void k_welford(const float* grad, float* mean, float* m2, int64_t n, float inv_k) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        const float delta = g - mean[i];
+        const float mu = mean[i] + delta * inv_k;
+        mean[i] = mu;
+        m2[i] += delta * (g - mu);
+    }
+}
+
+extern "C" int dgprf_welford_update(const float* grad, float* mean, float* m2, int64_t n, int k, void* stream) {
+    DGPRF_REQUIRE(grad && mean && m2 && n >= 0 && k >= 1, "welford_update: bad arguments");
+    if (n == 0) return DGPRF_OK;
+    int blocks = ceil_div(n, 256); if (blocks > 1184) blocks = 1184;
+    k_welford<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, mean, m2, n, 1.f / (float)k);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+struct MassTable { int64_t offset[DGPRF_MAX_SEGMENTS]; int64_t length[DGPRF_MAX_SEGMENTS]; };
+
+__global__ void __launch_bounds__(1024) k_mass_estimate(const float* mean, const float* m2, const __grid_constant__ MassTable tab,
+                                                        float denom, int centered, float* mass_out) {
+    __shared__ float red[32];
+    const int s = blockIdx.x;
+    const int64_t off = tab.offset[s], len = tab.length[s];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        const float var = m2[off + i] / denom;
+        acc += centered ? var : fmaf(mean[off + i], mean[off + i], var);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) mass_out[s] = sqrtf(acc / (float)len + 1.0e-7f);
+}
+
+extern "C" int dgprf_mass_estimate(const float* mean, const float* m2, const dgprf_segment* segs, int n_seg,
+                                   int K, int centered, float* mass_out, void* stream) {
+    DGPRF_REQUIRE(mean && m2 && segs && mass_out && n_seg >= 1 && n_seg <= DGPRF_MAX_SEGMENTS, "mass_estimate: bad arguments");
+    DGPRF_REQUIRE(K >= (centered ? 2 : 1), "mass_estimate: K_batches too small");
+    MassTable tab;
+    for (int s = 0; s < DGPRF_MAX_SEGMENTS; ++s) {
+        tab.offset[s] = s < n_seg ? segs[s].offset : 0;
+        tab.length[s] = s < n_seg ? segs[s].length : 0;
+    }
+    k_mass_estimate<<<n_seg, 1024, 0, (cudaStream_t)stream>>>(mean, m2, tab, centered ? (float)(K - 1) : (float)K,
+                                                              centered, mass_out);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- stand-alone GPLayer matmul: out[B,g] = Phi[B,F] @ W[F,g]; one warp per row -------------
+template <int GP>
+__global__ void __launch_bounds__(256) k_gp_matmul(const float* Phi, const float* W, int B, int F, int g, float* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= B) return;
+    float acc[GP];
+#pragma unroll
+    for (int j = 0; j < GP; ++j) acc[j] = 0.f;
+    for (int k = lane; k < F; k += 32) {
+        const float a = __ldg(Phi + row * F + k);
+#pragma unroll
+        for (int j = 0; j < GP; ++j)
+            if (j < g) acc[j] = fmaf(a, __ldg(W + (int64_t)k * g + j), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < GP; ++j) {
+        const float v = warp_sum(acc[j]);
+        if (lane == 0 && j < g) out[row * g + j] = v;
+    }
+}
+
+extern "C" int dgprf_gp_matmul(const float* Phi, const float* W, int B, int F, int g, float* out, void* stream) {
+    DGPRF_REQUIRE(Phi && W && out && B >= 0 && F >= 1 && g >= 1, "gp_matmul: bad arguments");
+    if (B == 0) return DGPRF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = ceil_div(B, 8);
+    switch (pad_g(g)) {
+        case 4:  k_gp_matmul<4><<<blocks, 256, 0, st>>>(Phi, W, B, F, g, out); break;
+        case 16: k_gp_matmul<16><<<blocks, 256, 0, st>>>(Phi, W, B, F, g, out); break;
+        case 32: k_gp_matmul<32><<<blocks, 256, 0, st>>>(Phi, W, B, F, g, out); break;
+        case 64: k_gp_matmul<64><<<blocks, 256, 0, st>>>(Phi, W, B, F, g, out); break;
+        default: dgprf_set_error("n_gp=%d > 64 unsupported", g); return DGPRF_EINVAL;
+    }
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
+// ---- debug/test hook: fill a buffer with the update kernel's Philox normals -----------------
+__global__ void k_philox_fill(float* out, int64_t n4, uint64_t seed, uint64_t chain, uint64_t step, uint32_t stream_id) {
+    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * blockDim.x)
+        *reinterpret_cast<float4*>(out + 4 * i4) = philox_normal4(seed, chain, (uint64_t)i4, step, stream_id);
+}
+
+extern "C" int dgprf_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t chain, uint64_t step,
+                                   int stream_id, void* stream) {
+    DGPRF_REQUIRE(out && n >= 0 && (n & 3) == 0, "philox_normal: n must be a multiple of 4");
+    if (n == 0) return DGPRF_OK;
+    int blocks = ceil_div(n >> 2, 256); if (blocks > 1184) blocks = 1184;
+    k_philox_fill<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n >> 2, seed, chain, step, (uint32_t)stream_id);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}

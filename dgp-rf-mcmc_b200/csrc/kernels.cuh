@@ -1,0 +1,48 @@
+// Kernel-argument structs and launcher prototypes shared between the .cu files and api.cu.
+#pragma once
+#include "common.cuh"
+
+struct LikArgs {
+    int32_t likelihood, B, D;
+    SlabMat F;                          // logits / means, ld = D
+    const float* Y; int64_t y_cs;       // [B, D] | [B, 1]
+    const float* lik_log_var; int64_t h_cs;   // Gaussian only
+    float* ll_rows; float* aux_rows;    // [C][B] nullable
+    float* ll_sum;                      // [C] nullable
+    float* dF; int64_t df_cs;           // [C][B][D] nullable (needs inv_B)
+    float* g_lik_log_var; int64_t g_cs; // nullable: dU/d lik_log_var (data term)
+    float* probs;                       // softmax only, nullable [C][B][D]
+    float inv_B;
+};
+
+struct UpdArgs {
+    float* theta; float* mom; int64_t cs; int64_t n;
+    const float* grad; int64_t grad_cs; int32_t n_part; int64_t part_stride;
+    int32_t n_seg;
+    float h, hN, beta, noise_scale /* sqrt(2(1-beta)T) */, inv_N;
+    int32_t resample;
+    uint64_t seed, step; uint32_t stream_base;
+    const float* eps_inject; const float* mom_inject;
+};
+
+struct HypArgs {
+    int32_t B, d, d_prev, d_x, g, ldx, has_mean;
+    SlabMat Fprev; const float* X; int64_t x_cs;
+    SlabMat T;      // raw T = dP z^T, ld = d
+    SlabMat R;      // rowsum(dP), ld = 1
+    SlabMat dF;     // dU/dF_l, ld = g
+    SlabMat Fcur;   // F_l, ld = g
+    const float* log_inv_ls; int64_t h_cs;
+    float* gH; int64_t gh_cs;
+    int64_t off_log_amp, off_log_inv_ls, off_mean;
+};
+
+int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
+int dgprf_launch_bwd_simt(const BwdArgs& a, int n_chains, cudaStream_t st);
+int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st);
+int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, int n_chains, cudaStream_t st);
+int dgprf_launch_sum_slabs(const SlabMat& m, int B, int ncol, float* out, int64_t out_cs, int n_chains, cudaStream_t st);
+int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_ss, int n_part,
+                               const float* theta, int64_t theta_cs, float inv_N,
+                               float* out, int64_t out_cs, int64_t n, int n_chains, cudaStream_t st);
+int dgprf_launch_hyper_reduce(const HypArgs& a, int n_chains, cudaStream_t st);
