@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the SG-MCMC sampling hot path (BASELINE.json: "SGHMC iters/sec ... 3-layer RF-DGP").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- 3-layer RBF RF-DGP regression on the synthetic
+UCI-protein shape (N=45730, D=9), M=512 random features, n_gp=[9,9,1], input concatenation, batch 1000,
+SGHMC (beta=0.9, T=1, lr=0.01), one chain per GPU.  A step is one `sgmcmc_update` on one minibatch:
+fused RF->GP forward x3, likelihood seed, backward x3, fused Philox update.
+
+  value   iterations/s with the dataset resident in HBM; every timed step is bracketed by its own CUDA
+          events on the launch stream and L2 is flushed (256 MiB write) between timed steps.
+  e2e     iterations/s through the public drop-in call `model.sgmcmc_update(X_batch, Y_batch, ...)` with
+          the minibatch in pinned HOST memory: H2D copy of the batch and D2H read of the minibatch
+          log-likelihood inside the timed region, back to back (no flush), barrier+sync on both sides.
+  N > 1   one process per GPU, independent chains (chain id = rank), no data-path collective: weak scaling.
+  --impl reference   the CPU restatement of the reference (oracle/, fp32 torch eager, all host threads):
+          TensorFlow cannot be installed offline, so the reference itself cannot run here.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dgp-rf-mcmc_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CFG = dict(workload="configs[1]: 3-layer RBF RF-DGP regression, synthetic UCI-protein shape",
+           N=45730, D=9, L=3, n_rf=512, n_gp=[9, 9, 1], input_cat=True, batch=1000,
+           sampler="SGHMC", lr=0.01, momentum_decay=0.9, temperature=1.0, chains_per_gpu=1)
+METRIC = "sghmc_iterations_per_second"
+UNIT = "it/s"
+
+
+def synthetic_protein(rank, device):
+    """X ~ N(0,1) [N,D]; Y = sin(X w) + 0.1 eps, standardised."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    X = torch.randn(CFG["N"], CFG["D"], generator=g)
+    w = torch.randn(CFG["D"], 1, generator=g)
+    Y = torch.sin(X @ w) + 0.1 * torch.randn(CFG["N"], 1, generator=g)
+    Y = (Y - Y.mean()) / Y.std()
+    return X.to(device), Y.to(device)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's fp32 eager step (op-for-op restatement of the reference's TF eager path)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s):
+    import dgprf_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    X = torch.randn(CFG["N"], CFG["D"], generator=g)
+    Y = torch.randn(CFG["N"], 1, generator=g)
+    p = O.init_params(CFG["D"], 1, CFG["L"], CFG["n_rf"], CFG["n_gp"], None, CFG["input_cat"], "gaussian",
+                      seed=1, dtype=torch.float32)
+    mom = {n: torch.randn(t.shape, generator=g) for n, t in p.w_named()}
+    B = CFG["batch"]
+    nb = CFG["N"] // B
+
+    def one(i):
+        lo = (i % nb) * B
+        O.eager_step_fp32(p, mom, X[lo:lo + B], Y[lo:lo + B], CFG["N"], CFG["lr"], CFG["momentum_decay"],
+                          CFG["temperature"], gen=g)
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps and (time.perf_counter() - t0) < budget_s:
+        one(warmup + done)
+        done += 1
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt, threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    its, done, dt, threads = cpu_reference_run(args.steps, max(args.warmup, 3), budget_s=60.0)
+    sample = f"{done} consecutive minibatch steps of the same workload in {dt:.1f} s (cap 60 s)"
+    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CFG,
+            "cpu_baseline": {"value": its, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "oracle/dgprf_oracle.py eager fp32 restatement; TensorFlow is not installable offline"},
+            "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_flops(spec, B):
+    """fwd = sum_l 2B(d_l M_l + F_l g_l); bwd_W = sum_l 4B F_l g_l + sum_{l>=1} 2B g_{l-1} M_l."""
+    fwd = [2.0 * B * (s.d * s.M + s.F * s.g) for s in spec.layers]
+    bwd = [4.0 * B * s.F * s.g + (2.0 * B * s.d_prev * s.M if l > 0 else 0.0) for l, s in enumerate(spec.layers)]
+    return fwd, bwd
+
+
+def run_ours(args, rank, world):
+    from dgprf import _ffi
+    from models.regression_model import RegressionDGP
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(100 + rank)
+    X, Y = synthetic_protein(rank, dev)
+    model = RegressionDGP(CFG["D"], 1, n_hidden_layers=CFG["L"], n_rf=CFG["n_rf"], n_gp=CFG["n_gp"],
+                          input_cat=CFG["input_cat"])
+    model.set_precision(args.precision)
+    model.seed(2024 + rank)
+    model.precond_update(None, CFG["N"], precond_type="identity")
+    e = model._engine
+    B, N = CFG["batch"], CFG["N"]
+    nb = N // B
+    kw = dict(lr=CFG["lr"], momentum_decay=CFG["momentum_decay"], temperature=CFG["temperature"])
+    launches_per_step = 2 * CFG["L"] + 2
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        lo = (i % nb) * B
+        model.sgmcmc_update(X[lo:lo + B], Y[lo:lo + B], N, **kw)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+
+    # ---- (1) value: resident inputs, per-step events, L2 flushed between timed steps -------------
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record(stream)
+        step(W + i)
+        ev[i][1].record(stream)
+    barrier()
+    wall_flushed = time.perf_counter() - t_wall0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    t_dev = sum(ms_steps) * 1e-3
+
+    # ---- (1b) warm, back-to-back loop (the sampler's real regime: state stays L2 resident) -------
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a0.record(stream)
+    for i in range(K):
+        step(W + K + i)
+    a1.record(stream)
+    barrier()
+    t_warm = a0.elapsed_time(a1) * 1e-3
+
+    # ---- (2) e2e: host (pinned) minibatches through the public call, H2D + D2H in the timed region
+    Xh, Yh = X.cpu().pin_memory(), Y.cpu().pin_memory()
+    xb = torch.empty(B, CFG["D"], device=dev); yb = torch.empty(B, 1, device=dev)
+    u_dev = torch.zeros(1, device=dev); u_host = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        lo = (i % nb) * B
+        xb.copy_(Xh[lo:lo + B], non_blocking=True)
+        yb.copy_(Yh[lo:lo + B], non_blocking=True)
+        model._step += 1
+        e.step(xb, yb, float(N), kw["lr"], kw["momentum_decay"], kw["temperature"], False, False,
+               model._seed, model._step, u_out=u_dev)
+        u_host.copy_(u_dev, non_blocking=True)
+
+    for i in range(W):
+        e2e_step(i)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b0.record(stream)
+    for i in range(K):
+        e2e_step(W + i)
+    b1.record(stream)
+    barrier()
+    t_e2e = b0.elapsed_time(b1) * 1e-3
+    clk = clocks.stop() if clocks else None
+    assert math.isfinite(float(u_host[0])), "sampler diverged"
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    times = torch.tensor([t_dev, t_warm, t_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_warm, t_e2e = (float(x) for x in times)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        # ---- per-kernel durations, live (CUDA events on the launch stream, inside libdgprf) --------
+        _ffi.profile_start()
+        PROF_STEPS = 50
+        for i in range(PROF_STEPS):
+            step(i)
+        recs = _ffi.profile_stop()
+        per = {}
+        for idx, (nm, ms) in enumerate(recs):
+            per.setdefault((nm, idx % launches_per_step), []).append(ms)
+        kernels = [{"kernel": nm, "slot": slot, "avg_us": 1e3 * statistics.mean(v)} for (nm, slot), v in sorted(per.items(), key=lambda kv: kv[0][1])]
+        step_us = sum(k["avg_us"] for k in kernels)
+        fwd_f, bwd_f = algorithmic_flops(e.spec, B)
+        L = CFG["L"]
+        for k in kernels:
+            s = k["slot"]
+            if s < L:
+                k["flops"] = fwd_f[s]; k["what"] = f"fwd layer {s}"
+            elif s == L:
+                k["what"] = "likelihood seed"
+            elif s <= 2 * L:
+                l = 2 * L - s
+                k["flops"] = bwd_f[l]; k["what"] = f"bwd layer {l}"
+            else:
+                k["bytes"] = 20.0 * e.layout.w_len; k["what"] = "sgmcmc update"
+            k["share"] = k["avg_us"] / step_us
+        dom = max(kernels, key=lambda k: k["avg_us"])
+        tf32_peak = pk["bf16_tflops"] / 2.0
+        if "flops" in dom:
+            ach = dom["flops"] / (dom["avg_us"] * 1e-6) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                    "traffic": None, "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
+                    "peak_source": f"{pk_src} bf16 burst / 2 (kind::tf32 rate); this round's kernel is the fp32 SIMT variant"}
+        else:
+            ach = dom["bytes"] / (dom["avg_us"] * 1e-6) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None, "kernel": dom["kernel"], "avg_us": dom["avg_us"], "peak_source": pk_src}
+
+        # ---- K5 on a >= 256 MiB flat buffer: the honest HBM number for the update kernel --------------
+        n_big = 16 << 20
+        Cn = 4                       # 4 chains x 16 Mi parameters x 4 B = 256 MiB per buffer
+        th = torch.randn(Cn, n_big, device=dev); mo = torch.randn(Cn, n_big, device=dev); gr = torch.randn(Cn, n_big, device=dev)
+        segs = _ffi.make_segments([(0, n_big, 1.0, 1)])
+        Lb = _ffi.lib()
+
+        def big(stepno):
+            _ffi.check(Lb.dgprf_sgmcmc_update(th.data_ptr(), mo.data_ptr(), n_big, n_big, Cn, gr.data_ptr(), n_big, 1, 0,
+                                              segs, 1, 1e-4, float(N), 0.9, 1.0, 0, 7, stepno, None, None, stream.cuda_stream))
+        for i in range(3):
+            big(i)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record(stream)
+        for i in range(10):
+            big(10 + i)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        k5_ms = c0.elapsed_time(c1) / 10
+        k5_gbs = 20.0 * Cn * n_big / (k5_ms * 1e-3) / 1e9
+        del th, mo, gr
+
+        # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------
+        cpu_its, cpu_done, cpu_dt, threads = cpu_reference_run(10 ** 9, 10, budget_s=15.0)
+
+        it_s = world * K / t_dev
+        line = {
+            "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(CFG, l2="flushed between timed steps (256 MiB write); per-step CUDA events",
+                           precision=("fp32 SIMT (DGPRF_PREC_FP32)" if args.precision == "fp32" else
+                                      "tf32 tcgen05 forward (3xTF32 phase GEMM, tf32 Phi*W), fp32 SIMT backward"), parallelism=f"{world} independent chain(s), 1 per GPU"),
+            "posterior_samples_per_second": it_s / (50 * nb),
+            "samples_note": f"cycle = 50 epochs x {nb} it (SURVEY 8d); excludes the per-sample test-set eval",
+            "warm_loop": {"value": world * K / t_warm, "unit": UNIT, "note": "back-to-back steps, no L2 flush, CPU launch cost included"},
+            "e2e": {"value": world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * B * (CFG["D"] + 1),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * K,
+            "launches_per_step": launches_per_step,
+            "roofline": roof,
+            "kernels": kernels,
+            "roofline_k5_256MiB": {"bound": "hbm", "achieved": k5_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": k5_gbs / pk["hbm_gbs"], "ms": k5_ms, "bytes": 20.0 * Cn * n_big,
+                                   "peak_source": pk_src},
+            "cpu_baseline": {"value": cpu_its, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{cpu_done} minibatch steps of the same workload in {cpu_dt:.1f} s"},
+            "clocks": clk,
+            "wall_s_flushed_loop": wall_flushed,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DGPRF_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for --impl ours (no CPU fallback); use --impl reference for the CPU arm")
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

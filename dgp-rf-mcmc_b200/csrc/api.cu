@@ -15,6 +15,53 @@ void dgprf_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dgprf_last_error(void) { return g_err; }
+
+// ---- measurement hook ---------------------------------------------------------------------------
+#include <vector>
+#include <string>
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+void dgprf_prof_begin(const char* name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof->push_back(r);
+}
+void dgprf_prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof->empty()) return;
+    cudaEventRecord(g_prof->back().b, st);
+}
+extern "C" int dgprf_profile_start(void) {
+    if (!g_prof) g_prof = new std::vector<ProfRec>();
+    for (auto& r : *g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof->clear();
+    g_prof_on = true;
+    return DGPRF_OK;
+}
+extern "C" int dgprf_profile_stop(int max_records, char* names, float* ms, int* n_out) {
+    g_prof_on = false;
+    DGPRF_REQUIRE(names && ms && n_out && max_records >= 0, "profile_stop: bad arguments");
+    int n = 0;
+    if (g_prof) {
+        for (auto& r : *g_prof) {
+            if (n < max_records) {
+                DGPRF_CHECK_CUDA(cudaEventSynchronize(r.b));
+                float t = 0.f;
+                DGPRF_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+                ms[n] = t;
+                snprintf(names + 32 * n, 32, "%s", r.name.c_str());
+                ++n;
+            }
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        g_prof->clear();
+    }
+    *n_out = n;
+    return DGPRF_OK;
+}
 extern "C" int dgprf_version(void) { return 100; }
 
 // ---- workspace layout ------------------------------------------------------------------------
@@ -161,7 +208,9 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
-        const int rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
+        const int rc = (m->precision == DGPRF_PREC_TF32 && dgprf_fwd_tc_supported(a))
+                           ? dgprf_launch_fwd_tc(a, m->n_chains, st)
+                           : dgprf_launch_fwd_simt(a, m->n_chains, st);
         if (rc) return rc;
     }
     if (F_out) {

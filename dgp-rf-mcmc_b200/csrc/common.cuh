@@ -25,6 +25,15 @@ void dgprf_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+// ---- measurement hook: CUDA events around every kernel launch (dgprf_profile_start/stop) ----
+void dgprf_prof_begin(const char* name, cudaStream_t st);
+void dgprf_prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    ProfScope(const char* name, cudaStream_t s) : st(s) { dgprf_prof_begin(name, s); }
+    ~ProfScope() { dgprf_prof_end(st); }
+};
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }
 
@@ -40,6 +49,7 @@ static inline int col_splits(int M) { int t = ceil_div(M, kTN); return t < kMaxC
 static inline int row_splits(int B) { int t = ceil_div(B, kTM); return t < kMaxRS ? t : kMaxRS; }
 static inline int pad_g(int g) { return g <= 4 ? 4 : g <= 16 ? 16 : g <= 32 ? 32 : g <= 64 ? 64 : -1; }
 
+
 // A matrix given as a sum of `n_slabs` partial slabs: value(c,row,col) =
 // sum_s ptr[c*cs + s*ss + row*ld + col].  n_slabs==1 is a plain dense matrix.
 struct SlabMat {
@@ -50,10 +60,15 @@ struct SlabMat {
     int32_t n_slabs;
 };
 
+// All slab loads are issued before the (fixed-order) adds so they overlap: n_slabs <= kMaxCS.
 __device__ __forceinline__ float slab_load(const SlabMat& m, int chain, int64_t row, int col) {
     const float* p = m.ptr + chain * m.cs + row * m.ld + col;
-    float v = 0.f;
-    for (int s = 0; s < m.n_slabs; ++s) v += __ldg(p + s * m.ss);
+    float t[kMaxCS];
+#pragma unroll
+    for (int s = 0; s < kMaxCS; ++s) t[s] = s < m.n_slabs ? __ldg(p + s * m.ss) : 0.f;
+    float v = t[0];
+#pragma unroll
+    for (int s = 1; s < kMaxCS; ++s) v += t[s];
     return v;
 }
 
@@ -102,6 +117,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     }
     return r;
 }
+
+// 4-byte async copy global -> shared (LDGSTS); !pred zero-fills the destination.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // sin/cos with a 2-constant Cody-Waite reduction to [-pi, pi] followed by the MUFU
 // approximations (abs error ~5e-7 on the reduced range).  Random-feature phases reach

@@ -8,6 +8,8 @@
 // P never reaches HBM.  A CTA owns a 64-row tile and every CS-th 64-column tile of the random
 // features; it writes Phi (optionally, for the backward) and ONE partial slab of F.  The CS
 // slabs are summed, in fixed order, by whoever reads F next (deterministic, no atomics).
+// Latency structure: the W tile of GEMM #2 is fetched with cp.async while GEMM #1 runs, and
+// every global load of a phase is in flight before the first one is consumed.
 #include "kernels.cuh"
 
 template <int GP>
@@ -20,8 +22,6 @@ k1_fwd_simt(const FwdArgs a) {
     float* om_s  = in_s + kTM * LDI;           // [kKC][kTN]
     float* phi_s = om_s + kKC * kTN;           // [kTM][LDP]   (also the cross-quarter reduction buffer)
     float* w_s   = phi_s + kTM * LDP;          // [2*kTN][GP]
-    float* s_all = w_s + 2 * kTN * GP;         // [d] exp(log_inv_ls)
-    float* m_all = s_all + a.d;                // [d] mean
 
     const int tid = threadIdx.x;
     const int chain = blockIdx.z;
@@ -38,12 +38,6 @@ k1_fwd_simt(const FwdArgs a) {
     const bool rbf = a.kind == DGPRF_KIND_RBF;
     const float scale = (rbf ? 1.f : 1.41421356237f) * amp * rsqrtf((float)a.M);
 
-    for (int q = tid; q < a.d; q += kThreads) {
-        s_all[q] = expf(__ldg(ls + q));
-        m_all[q] = mean ? __ldg(mean + q) : 0.f;
-    }
-    __syncthreads();
-
     const int KT = rbf ? 2 * kTN : kTN;        // K extent of GEMM #2 per column tile
     const int r2 = tid & (kTM - 1), kq = tid >> 6;
     float acc2[GP];
@@ -53,6 +47,15 @@ k1_fwd_simt(const FwdArgs a) {
     const int n_ct = (a.M + kTN - 1) / kTN;
     for (int ct = cs; ct < n_ct; ct += a.CS) {
         const int c0 = ct * kTN;
+        if (a.do_gemm2) {                       // W tile of this column tile: async, consumed after GEMM #1
+            for (int e = tid; e < KT * GP; e += kThreads) {
+                const int k = e / GP, j = e % GP;
+                const int col = c0 + (k < kTN ? k : k - kTN);
+                const int64_t frow = (k < kTN ? 0 : a.M) + col;
+                cp_async4(w_s + e, W + frow * a.g + j, col < a.M && j < a.g);
+            }
+            cp_async_commit();
+        }
         float p[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -60,24 +63,37 @@ k1_fwd_simt(const FwdArgs a) {
             for (int j = 0; j < 4; ++j) p[i][j] = 0.f;
 
         for (int k0 = 0; k0 < a.d; k0 += kKC) {
-            for (int e = tid; e < kTM * kKC; e += kThreads) {
+            float vin[kTM * kKC / kThreads], vom[kKC * kTN / kThreads];
+#pragma unroll
+            for (int u = 0; u < kTM * kKC / kThreads; ++u) {
+                const int e = tid + u * kThreads;
                 const int r = e / kKC, k = e % kKC, q = k0 + k;
                 const int64_t row = row0 + r;
                 float v = 0.f;
                 if (row < a.B && q < a.d)
                     v = q < a.d_prev ? slab_load(a.Fprev, chain, row, q)
                                      : __ldg(X + row * a.ldx + (q - a.d_prev));
-                in_s[r * LDI + k] = v;
+                vin[u] = v;
             }
-            for (int e = tid; e < kKC * kTN; e += kThreads) {
+#pragma unroll
+            for (int u = 0; u < kKC * kTN / kThreads; ++u) {
+                const int e = tid + u * kThreads;
                 const int k = e / kTN, c = e % kTN, q = k0 + k, col = c0 + c;
                 float v = 0.f;
-                if (q < a.d && col < a.M) v = fmaf(s_all[q], __ldg(z + (int64_t)q * a.M + col), m_all[q]);
-                om_s[k * kTN + c] = v;
+                if (q < a.d && col < a.M)
+                    v = fmaf(expf(__ldg(ls + q)), __ldg(z + (int64_t)q * a.M + col), mean ? __ldg(mean + q) : 0.f);
+                vom[u] = v;
             }
+#pragma unroll
+            for (int u = 0; u < kTM * kKC / kThreads; ++u) {
+                const int e = tid + u * kThreads;
+                in_s[(e / kKC) * LDI + (e % kKC)] = vin[u];
+            }
+#pragma unroll
+            for (int u = 0; u < kKC * kTN / kThreads; ++u) om_s[tid + u * kThreads] = vom[u];
             __syncthreads();
-#pragma unroll 8
-            for (int k = 0; k < kKC; ++k) {
+            const int kmax = min(kKC, a.d - k0);
+            for (int k = 0; k < kmax; ++k) {
                 const float4 b = *reinterpret_cast<const float4*>(om_s + k * kTN + tx * 4);
                 float av[4];
 #pragma unroll
@@ -130,14 +146,7 @@ k1_fwd_simt(const FwdArgs a) {
                 }
             }
         }
-        if (a.do_gemm2) {
-            for (int e = tid; e < KT * GP; e += kThreads) {
-                const int k = e / GP, j = e % GP;
-                const int col = c0 + (k < kTN ? k : k - kTN);
-                const int64_t frow = (k < kTN ? 0 : a.M) + col;
-                w_s[e] = (col < a.M && j < a.g) ? __ldg(W + frow * a.g + j) : 0.f;
-            }
-        }
+        cp_async_wait_all();
         __syncthreads();
         if (a.do_gemm2) {
             const int kb = kq * (KT / 4);
@@ -181,26 +190,25 @@ k1_fwd_simt(const FwdArgs a) {
     }
 }
 
-static size_t fwd_smem_bytes(int GP, int d) {
-    return sizeof(float) * (size_t)(kTM * (kKC + 1) + kKC * kTN + kTM * (2 * kTN + 1) + 2 * kTN * GP + 2 * d);
+static size_t fwd_smem_bytes(int GP) {
+    return sizeof(float) * (size_t)(kTM * (kKC + 1) + kKC * kTN + kTM * (2 * kTN + 1) + 2 * kTN * GP);
 }
 
 template <int GP>
 static int launch_fwd(const FwdArgs& a, int n_chains, cudaStream_t st) {
-    const size_t smem = fwd_smem_bytes(GP, a.d);
-    static size_t configured = 0;
-    if (smem > configured) {
+    const size_t smem = fwd_smem_bytes(GP);
+    static bool configured = false;
+    if (!configured) {
         DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_simt<GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured = true;
     }
     dim3 grid(ceil_div(a.B, kTM), a.CS, n_chains);
-    k1_fwd_simt<GP><<<grid, kThreads, smem, st>>>(a);
+    { ProfScope _ps("k1_fwd_simt", st); k1_fwd_simt<GP><<<grid, kThreads, smem, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
 
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st) {
-    DGPRF_REQUIRE(a.d <= 8192, "RF layer input width %d > 8192 unsupported", a.d);
     switch (pad_g(a.do_gemm2 ? a.g : 1)) {
         case 4:  return launch_fwd<4>(a, n_chains, st);
         case 16: return launch_fwd<16>(a, n_chains, st);

@@ -44,11 +44,14 @@ k2_bwd_simt(const BwdArgs a) {
     const float arc_scale = 1.41421356237f * amp * rsqrtf((float)a.M);
     const bool need_R = a.has_mean || a.hyper;
     const int dq = a.hyper ? a.d : a.d_prev;   // T columns that somebody consumes
+    const bool z_once = dq <= kTN;              // a single T pass: stage z once per column tile
 
     for (int q = tid; q < a.d; q += kThreads) {
         s_all[q] = expf(__ldg(ls + q));
         m_all[q] = mean ? __ldg(mean + q) : 0.f;
     }
+    // 16-byte async copies of Phi need M % 4 == 0 (rows of Phi and the sin block stay 16 B aligned)
+    const bool phi_vec = (a.M % 4 == 0) && ((a.phi_cs % 4) == 0);
 
     const int n_ct = (a.M + kTN - 1) / kTN, n_rt = (a.B + kTM - 1) / kTM;
     // gW phase mapping: feature f of the 128 (64 cos|relu + 64 sin), half jh of the outputs
@@ -63,9 +66,16 @@ k2_bwd_simt(const BwdArgs a) {
             const int c = e / GP, k = e % GP;      // coalesced along a W row
             const int col = c0 + c;
             const bool ok = col < a.M && k < a.g;
-            wcT_s[k * kTN + c] = ok ? __ldg(W + (int64_t)col * a.g + k) : 0.f;
-            wsT_s[k * kTN + c] = (ok && rbf) ? __ldg(W + (int64_t)(a.M + col) * a.g + k) : 0.f;
+            cp_async4(wcT_s + k * kTN + c, W + (int64_t)col * a.g + k, ok);
+            cp_async4(wsT_s + k * kTN + c, W + (int64_t)(a.M + col) * a.g + k, ok && rbf);
         }
+        if (z_once && dq > 0) {                    // the z tile depends on the column tile only
+            for (int e = tid; e < kTN * kTN; e += kThreads) {
+                const int qq = e / kTN, c = e % kTN;
+                cp_async4(z_s + qq * LDZ + c, z + (int64_t)qq * a.M + c0 + c, qq < a.d && (c0 + c) < a.M);
+            }
+        }
+        cp_async_commit();
         float accg[GH];
 #pragma unroll
         for (int j = 0; j < GH; ++j) accg[j] = 0.f;
@@ -73,18 +83,37 @@ k2_bwd_simt(const BwdArgs a) {
         for (int rt = rs; rt < n_rt; rt += a.RS) {
             const int row0 = rt * kTM;
             __syncthreads();
-            for (int e = tid; e < kTM * GP; e += kThreads) {
-                const int r = e / GP, k = e % GP;
-                const int64_t row = row0 + r;
-                dF_s[e] = (row < a.B && k < a.g) ? slab_load(a.dF, chain, row, k) : 0.f;
+            if (phi_vec) {
+                for (int e = tid; e < kTM * (kTN / 4); e += kThreads) {
+                    const int r = e / (kTN / 4), c = (e % (kTN / 4)) * 4;
+                    const int64_t row = row0 + r;
+                    const bool ok = row < a.B && (c0 + c) < a.M;
+                    cp_async16(phc_s + r * LDT + c, Phi + row * a.F + c0 + c, ok);
+                    cp_async16(phs_s + r * LDT + c, Phi + row * a.F + a.M + c0 + c, ok && rbf);
+                }
+            } else {
+                for (int e = tid; e < kTM * kTN; e += kThreads) {
+                    const int r = e / kTN, c = e % kTN;
+                    const int64_t row = row0 + r;
+                    const bool ok = row < a.B && (c0 + c) < a.M;
+                    cp_async4(phc_s + r * LDT + c, Phi + row * a.F + c0 + c, ok);
+                    cp_async4(phs_s + r * LDT + c, Phi + row * a.F + a.M + c0 + c, ok && rbf);
+                }
             }
-            for (int e = tid; e < kTM * kTN; e += kThreads) {
-                const int r = e / kTN, c = e % kTN;
-                const int64_t row = row0 + r;
-                const bool ok = row < a.B && (c0 + c) < a.M;
-                phc_s[r * LDT + c] = ok ? __ldg(Phi + row * a.F + c0 + c) : 0.f;
-                phs_s[r * LDT + c] = (ok && rbf) ? __ldg(Phi + row * a.F + a.M + c0 + c) : 0.f;
+            cp_async_commit();
+            {
+                float v[kTM * GP / kThreads];
+#pragma unroll
+                for (int u = 0; u < kTM * GP / kThreads; ++u) {
+                    const int e = tid + u * kThreads;
+                    const int r = e / GP, k = e % GP;
+                    const int64_t row = row0 + r;
+                    v[u] = (row < a.B && k < a.g) ? slab_load(a.dF, chain, row, k) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kTM * GP / kThreads; ++u) dF_s[tid + u * kThreads] = v[u];
             }
+            cp_async_wait_all();
             __syncthreads();
 
             // ---- dPhi = dF W^T on a 4x4 micro-tile, then dP ----
@@ -158,12 +187,14 @@ k2_bwd_simt(const BwdArgs a) {
 
             // ---- T = dP z^T in passes of 64 input columns ----
             for (int q0 = 0; q0 < dq; q0 += kTN) {
-                for (int e = tid; e < kTN * kTN; e += kThreads) {
-                    const int qq = e / kTN, c = e % kTN;
-                    const int q = q0 + qq, col = c0 + c;
-                    z_s[qq * LDZ + c] = (q < a.d && col < a.M) ? __ldg(z + (int64_t)q * a.M + col) : 0.f;
+                if (!z_once) {
+                    for (int e = tid; e < kTN * kTN; e += kThreads) {
+                        const int qq = e / kTN, c = e % kTN;
+                        const int q = q0 + qq, col = c0 + c;
+                        z_s[qq * LDZ + c] = (q < a.d && col < a.M) ? __ldg(z + (int64_t)q * a.M + col) : 0.f;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 float t[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -234,7 +265,7 @@ static int launch_bwd(const BwdArgs& a, int n_chains, cudaStream_t st) {
         configured = smem;
     }
     dim3 grid(a.RS, a.CS, n_chains);
-    k2_bwd_simt<GP><<<grid, kThreads, smem, st>>>(a);
+    { ProfScope _ps("k2_bwd_simt", st); k2_bwd_simt<GP><<<grid, kThreads, smem, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }

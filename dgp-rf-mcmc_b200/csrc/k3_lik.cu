@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st) {
     DGPRF_REQUIRE(a.likelihood == DGPRF_LIK_GAUSSIAN || a.D <= kMaxClasses,
                   "softmax with %d classes > %d unsupported", a.D, kMaxClasses);
-    k3_loglik<<<n_chains, kLikThreads, 0, st>>>(a);
+    { ProfScope _ps("k3_loglik", st); k3_loglik<<<n_chains, kLikThreads, 0, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }

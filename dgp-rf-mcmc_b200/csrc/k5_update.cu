@@ -42,9 +42,14 @@ __global__ void __launch_bounds__(256) k5_sgmcmc_update(const UpdArgs a, const _
         float4 th = *reinterpret_cast<const float4*>(theta + i);
         float4 m = *reinterpret_cast<const float4*>(mom + i);
         float4 g = __ldg(reinterpret_cast<const float4*>(grad + i));
-        for (int p = 1; p < a.n_part; ++p) {
-            const float4 gp = __ldg(reinterpret_cast<const float4*>(grad + p * a.part_stride + i));
-            g.x += gp.x; g.y += gp.y; g.z += gp.z; g.w += gp.w;
+        for (int p0 = 1; p0 < a.n_part; p0 += 8) {        // 8 partial slabs in flight, fixed-order adds
+            float4 gp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                gp[u] = (p0 + u) < a.n_part ? __ldg(reinterpret_cast<const float4*>(grad + (p0 + u) * a.part_stride + i))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { g.x += gp[u].x; g.y += gp[u].y; g.z += gp[u].z; g.w += gp[u].w; }
         }
         if (prior) {
             g.x = fmaf(th.x, a.inv_N, g.x); g.y = fmaf(th.y, a.inv_N, g.y);
@@ -100,7 +105,7 @@ int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid(blocks, n_chains);
-    k5_sgmcmc_update<<<grid, 256, 0, st>>>(a, tab);
+    { ProfScope _ps("k5_sgmcmc_update", st); k5_sgmcmc_update<<<grid, 256, 0, st>>>(a, tab); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }

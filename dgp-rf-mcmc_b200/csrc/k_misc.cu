@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_hyper_reduce(const HypArgs a) {
 
 int dgprf_launch_hyper_reduce(const HypArgs& a, int n_chains, cudaStream_t st) {
     dim3 grid((a.d + 31) / 32 + 1, n_chains);
-    k_hyper_reduce<<<grid, 256, 0, st>>>(a);
+    { ProfScope _ps("k8_hyper_reduce", st); k_hyper_reduce<<<grid, 256, 0, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }

@@ -76,6 +76,8 @@ SIGNATURES = {
     "dgprf_gaussian_log_prob": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
     "dgprf_softmax_log_prob": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "dgprf_philox_normal": (_I, [_VP, _I64, _U64, _U64, _U64, _I, _VP]),
+    "dgprf_profile_start": (_I, []),
+    "dgprf_profile_stop": (_I, [_I, C.c_char_p, C.POINTER(C.c_float), C.POINTER(_I)]),
 }
 
 
@@ -128,6 +130,20 @@ def as_dev(x, device, dtype=torch.float32) -> torch.Tensor:
     if x.dtype != dtype or x.device != device:
         x = x.to(device=device, dtype=dtype)
     return x.contiguous()
+
+
+def profile_start():
+    check(lib().dgprf_profile_start())
+
+
+def profile_stop(max_records=4096):
+    """-> list of (kernel name, milliseconds) in launch order."""
+    names = C.create_string_buffer(32 * max_records)
+    ms = (C.c_float * max_records)()
+    n = C.c_int(0)
+    check(lib().dgprf_profile_stop(max_records, names, ms, C.byref(n)))
+    raw = names.raw
+    return [(raw[32 * i:32 * i + 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
 
 
 def make_segments(entries) -> "C.Array[Segment]":

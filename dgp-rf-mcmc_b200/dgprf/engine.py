@@ -96,10 +96,13 @@ class Engine:
     """Owns the flat buffers of C chains of one architecture and drives libdgprf."""
 
     def __init__(self, spec: ModelSpec, n_chains: int = 1, device: Optional[torch.device] = None,
-                 precision: int = _ffi.PREC_FP32, z: Optional[List[torch.Tensor]] = None, shared_z: bool = True):
+                 precision: Optional[int] = None, z: Optional[List[torch.Tensor]] = None, shared_z: bool = True):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
                 else torch.device("cpu")
+        if precision is None:
+            from . import default_precision
+            precision = default_precision()
         self.spec, self.C, self.device, self.precision = spec, int(n_chains), device, precision
         self.layout = FlatLayout.of(spec)
         f32 = dict(device=device, dtype=torch.float32)
@@ -162,6 +165,10 @@ class Engine:
     def named_from_flat(self, flat: torch.Tensor, which: str, chain: int = 0) -> Dict[str, torch.Tensor]:
         segs = self.seg_w if which == "w" else self.seg_h
         return {n: flat[chain, s[0]:s[0] + s[1]].clone() for n, s in segs.items()}
+
+    def set_precision(self, name: str):
+        self.precision = {"fp32": _ffi.PREC_FP32, "tf32": _ffi.PREC_TF32}[name]
+        self._model = None
 
     def set_mass(self, name: str, mass: float):
         (self.seg_w if name in self.seg_w else self.seg_h)[name][2] = float(mass)

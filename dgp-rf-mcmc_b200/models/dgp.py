@@ -134,6 +134,10 @@ class DGP_RF:
     def _set_mass(self, var, mass):
         self._engine.set_mass(var._seg, mass)
 
+    def set_precision(self, name):
+        """'fp32' (SIMT, parity mode) | 'tf32' (tcgen05 tensor-core kernels).  Extension."""
+        self._engine.set_precision(name)
+
     def seed(self, seed):
         """Seed of the in-kernel Philox noise (extension; the reference is unseeded)."""
         self._seed, self._step = int(seed), 0

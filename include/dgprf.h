@@ -207,6 +207,12 @@ int dgprf_softmax_log_prob(const float* F, const float* Y, int B, int C, float* 
 int dgprf_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t chain, uint64_t step,
                         int stream_id, void* stream);
 
+/* Measurement hook (bench.py): between start and stop every kernel launched by this thread is
+ * bracketed by CUDA events on its launch stream; stop synchronises them and returns up to
+ * max_records (name[32], milliseconds) pairs in launch order.  Not for production loops. */
+int dgprf_profile_start(void);
+int dgprf_profile_stop(int max_records, char* names, float* ms, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""Tensor-core path (DGPRF_PREC_TF32: tcgen05 kind::tf32 + TMEM + TMA store) against the fp64 oracle.
+
+Stated bound for this mode (BASELINE.json north_star: "a looser stated bound if TF32/bf16 tensor-core
+modes are enabled"): the phase GEMM X*Omega runs as 3xTF32 (fp32-accurate, so ReLU gates and phases
+match), the Phi*W GEMM as plain tf32 (operands carry a 10-bit mantissa, relative 2^-11).  Layer
+outputs, log-likelihoods and gradients agree with the oracle to max-abs error / max-abs reference
+<= 3e-3; saved features to 1e-4.  Exception, stated: with arc-cosine (ReLU) layers the gradients of
+UPSTREAM layers are only bounded by 5e-2 -- the tf32 error of F (~3e-4) flips about 0.02 % of the
+downstream ReLU gates and the derivative is discontinuous there (the gradient is exact for the
+perturbed forward).  The fp32 SIMT mode keeps the 1e-4 bound for everything (tests/test_parity_gpu.py)."""
+import pytest
+import torch
+
+import dgprf_oracle as O
+from dgprf import _ffi
+from dgprf.engine import Engine, ModelSpec
+from helpers import oracle_params, rel_err
+from models.classification_model import ClassificationDGP
+from models.regression_model import RegressionDGP
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 3e-3
+ARC_UPSTREAM_GRAD_TOL = 5e-2
+
+CASES = {
+    # name: (cls, d_in, d_out, L, n_rf, n_gp, kinds, input_cat, mean, B)
+    "protein_full_layer": (RegressionDGP, 9, 1, 3, 512, [9, 9, 1], None, True, False, 1000),
+    "arc_softmax": (ClassificationDGP, 40, 10, 3, 256, [30, 30, 10], ["ARC"] * 3, True, False, 300),
+    "two_tiles_per_cta_mean": (RegressionDGP, 5, 2, 2, [1024, 68], [40, 2], ["RBF", "ARC"], True, True, 130),
+    "wide_input_kgroups": (ClassificationDGP, 200, 4, 2, 128, [33, 4], ["ARC", "RBF"], True, False, 257),
+    "tiny": (RegressionDGP, 1, 1, 2, 100, [1, 1], None, False, False, 20),
+}
+
+
+def build(name):
+    cls, d_in, d_out, L, n_rf, n_gp, kinds, cat, mean, B = CASES[name]
+    torch.manual_seed(0)
+    model = cls(d_in, d_out, n_hidden_layers=L, n_rf=n_rf, n_gp=n_gp, kernel_type_list=kinds, input_cat=cat,
+                set_nonzero_mean=mean)
+    if mean:
+        for l in range(L):
+            model._vars[f"mean_{l}"].assign(0.3 * torch.randn(model._engine.spec.layers[l].d, 1))
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(B, d_in, generator=g)
+    Y = torch.randn(B, d_out, generator=g) if cls is RegressionDGP else torch.randint(0, d_out, (B, 1), generator=g).float()
+    return model, X, Y
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tc_forward_matches_oracle_and_simt(name):
+    model, X, Y = build(name)
+    p = oracle_params(model)
+    F_ref = O.bnn_forward(p, X.double())
+    F32 = model.BNN(X).clone()
+    model.set_precision("tf32")
+    Ftc = model.BNN(X)
+    assert rel_err(F32, F_ref) < 1e-4
+    assert rel_err(Ftc, F_ref) < TF32_TOL
+    ll_ref = O.log_likelihood(p, X.double(), Y.double())
+    assert rel_err(model.log_likelihood(X, Y), ll_ref) < TF32_TOL
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tc_saved_features_and_gradients(name):
+    """TRAIN mode: Phi is written by the TMA store; the backward consumes it."""
+    model, X, Y = build(name)
+    model.set_precision("tf32")
+    p = oracle_params(model)
+    N = 5000
+    u_ref, g_ref = O.grads_autograd(p, X.double(), Y.double(), N, False)
+    u, g = model.grad_U(X, Y, N)
+    assert float(u) == pytest.approx(float(u_ref), rel=TF32_TOL)
+    kinds = CASES[name][6] or []
+    last = f"W_{CASES[name][3] - 1}"
+    for n, ref in g_ref.items():
+        tol = ARC_UPSTREAM_GRAD_TOL if ("ARC" in kinds and n != last) else TF32_TOL
+        assert rel_err(g[n], ref) < tol, n
+    # the saved features themselves
+    e = model._engine
+    Fs, Phis = O.bnn_forward(p, X.double(), return_all=True)
+    import ctypes as C
+    m = e.model()
+    ws = e.workspace(m, X.shape[0], _ffi.MODE_TRAIN)
+    # layer-0 Phi sits right after layer-0's F partial slabs in the workspace (csrc/api.cu make_layout)
+    s0 = e.spec.layers[0]
+    CS = min((s0.M + 63) // 64, 8)
+    off = ((CS * X.shape[0] * s0.g * 4 + 255) // 256) * 256
+    Phi0 = ws[off:off + X.shape[0] * s0.F * 4].view(torch.float32).view(X.shape[0], s0.F)
+    assert rel_err(Phi0, Phis[0]) < 1e-4
+
+
+def test_tc_multi_chain_matches_single_chain():
+    spec = ModelSpec.build(9, 1, [256] * 2, [9, 1], ["RBF"] * 2, True, False, "gaussian")
+    torch.manual_seed(3)
+    e = Engine(spec, 3, precision=_ffi.PREC_TF32, shared_z=False)
+    for off, ln, _, _ in e.seg_w.values():
+        e.theta_w[:, off:off + ln].normal_()
+    e.theta_h[:, e.layout.off_lik_log_var] = -2.0
+    X = torch.randn(3, 200, 9, device="cuda"); Y = torch.randn(3, 200, 1, device="cuda")
+    tot, gW, _ = e.gradients(X, Y, 1000.0, hyper=False, prior_w=True, prior_h=False)
+    c = 2
+    e1 = Engine(spec, 1, precision=_ffi.PREC_TF32, z=[z[c:c + 1].clone() for z in e.z])
+    e1.theta_w.copy_(e.theta_w[c:c + 1]); e1.theta_h.copy_(e.theta_h[c:c + 1])
+    t1, g1, _ = e1.gradients(X[c], Y[c], 1000.0, hyper=False, prior_w=True, prior_h=False)
+    assert torch.equal(g1[0], gW[c]) and torch.equal(t1[0], tot[c])
+
+
+def test_tc_sampling_step():
+    model, X, Y = build("protein_full_layer")
+    model.set_precision("tf32")
+    N = 45730
+    model.precond_update(None, N, precond_type="identity")
+    e = model._engine
+    p = oracle_params(model)
+    names = e.names(False)
+    g = torch.Generator().manual_seed(7)
+    mom = {n: e.view(n, "mom").double().cpu().clone() for n in names}
+    eps = {n: torch.randn(e.view(n).shape, generator=g, dtype=torch.float64) for n in names}
+    _, _, p_new, m_new = O.sgmcmc_step(p, mom, X.double(), Y.double(), N, lr=0.02, momentum_decay=0.9, eps=eps)
+    model.sgmcmc_update(X, Y, N, lr=0.02, momentum_decay=0.9, eps=eps)
+    new = dict(p_new.w_named())
+    for n in names:
+        assert rel_err(e.view(n), new[n]) < TF32_TOL, n
+        assert rel_err(e.view(n, "mom"), m_new[n]) < TF32_TOL, n
