@@ -251,14 +251,14 @@ class Engine:
         return X, x_cs, Y, y_cs, B
 
     # ---- hot path ------------------------------------------------------------------------------------
-    def forward(self, X, m: Optional[_ffi.Model] = None) -> torch.Tensor:
-        """BNN(X): [C, B, d_out] (utils.py:10-16, 32-44)."""
+    def forward(self, X, m: Optional[_ffi.Model] = None, mode: int = _ffi.MODE_EVAL, want_F: bool = True):
+        """BNN(X): [C, B, d_out] (utils.py:10-16, 32-44).  mode=TRAIN also saves the features."""
         m = self.model() if m is None else m
         X, x_cs, _, _, B = self._xy(X, None, m.n_chains)
-        ws = self.workspace(m, B, _ffi.MODE_EVAL)
-        F = torch.empty(m.n_chains, B, self.spec.d_out, device=self.device, dtype=torch.float32)
-        _ffi.check(_ffi.lib().dgprf_forward(C.byref(m), X.data_ptr(), x_cs, B, _ffi.MODE_EVAL, ws.data_ptr(),
-                                            ws.numel(), F.data_ptr(), _ffi.stream_ptr()))
+        ws = self.workspace(m, B, mode)
+        F = torch.empty(m.n_chains, B, self.spec.d_out, device=self.device, dtype=torch.float32) if want_F else None
+        _ffi.check(_ffi.lib().dgprf_forward(C.byref(m), X.data_ptr(), x_cs, B, mode, ws.data_ptr(),
+                                            ws.numel(), _ffi.ptr(F), _ffi.stream_ptr()))
         return F
 
     def evaluate(self, X, Y, m: Optional[_ffi.Model] = None):
