@@ -173,7 +173,7 @@ def run_ours(args, rank, world):
     B, N = CFG["batch"], CFG["N"]
     nb = N // B
     kw = dict(lr=CFG["lr"], momentum_decay=CFG["momentum_decay"], temperature=CFG["temperature"])
-    launches_per_step = 2 * CFG["L"] + 2
+    launches_per_step = 1 if args.precision == "fp32" else 2 * CFG["L"] + 2     # row-fused step with fused update | layered
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -218,17 +218,13 @@ def run_ours(args, rank, world):
 
     # ---- (2) e2e: host (pinned) minibatches through the public call, H2D + D2H in the timed region
     Xh, Yh = X.cpu().pin_memory(), Y.cpu().pin_memory()
-    xb = torch.empty(B, CFG["D"], device=dev); yb = torch.empty(B, 1, device=dev)
-    u_dev = torch.zeros(1, device=dev); u_host = torch.zeros(1).pin_memory()
+    u_host = torch.zeros(1).pin_memory()
 
     def e2e_step(i):
+        # the public drop-in call on a HOST minibatch: H2D of X_b, Y_b, the step, and the D2H read of the
+        # minibatch log-likelihood are all inside the timed region (dgprf_sgmcmc_step_host)
         lo = (i % nb) * B
-        xb.copy_(Xh[lo:lo + B], non_blocking=True)
-        yb.copy_(Yh[lo:lo + B], non_blocking=True)
-        model._step += 1
-        e.step(xb, yb, float(N), kw["lr"], kw["momentum_decay"], kw["temperature"], False, False,
-               model._seed, model._step, u_out=u_dev)
-        u_host.copy_(u_dev, non_blocking=True)
+        model.sgmcmc_update(Xh[lo:lo + B], Yh[lo:lo + B], N, u_host=u_host, **kw)
 
     for i in range(W):
         e2e_step(i)
@@ -266,7 +262,10 @@ def run_ours(args, rank, world):
         L = CFG["L"]
         for k in kernels:
             s = k["slot"]
-            if s < L:
+            if launches_per_step == 1:
+                k["flops"] = sum(fwd_f) + sum(bwd_f)
+                k["what"] = "row-fused step: forward + likelihood seed + backward (all layers) + grid barrier + update"
+            elif s < L:
                 k["flops"] = fwd_f[s]; k["what"] = f"fwd layer {s}"
             elif s == L:
                 k["what"] = "likelihood seed"
@@ -282,7 +281,9 @@ def run_ours(args, rank, world):
             ach = dom["flops"] / (dom["avg_us"] * 1e-6) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                     "traffic": None, "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
-                    "peak_source": f"{pk_src} bf16 burst / 2 (kind::tf32 rate); this round's kernel is the fp32 SIMT variant"}
+                    "peak_source": f"{pk_src} bf16 burst / 2 (kind::tf32 rate)",
+                    "note": "configs[1] is latency-bound (0.18 GFLOP per step): see roofline_k5_256MiB and DESIGN.md section 5 "
+                            "for the kernels at bandwidth/throughput-relevant sizes"}
         else:
             ach = dom["bytes"] / (dom["avg_us"] * 1e-6) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
@@ -320,7 +321,7 @@ def run_ours(args, rank, world):
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(CFG, l2="flushed between timed steps (256 MiB write); per-step CUDA events",
-                           precision=("fp32 SIMT (DGPRF_PREC_FP32)" if args.precision == "fp32" else
+                           precision=("fp32: one cooperative row-fused step kernel per iteration (8-row groups through all layers, update behind a grid barrier)" if args.precision == "fp32" else
                                       "tf32 tcgen05 forward (3xTF32 phase GEMM, tf32 Phi*W), fp32 SIMT backward"), parallelism=f"{world} independent chain(s), 1 per GPU"),
             "posterior_samples_per_second": it_s / (50 * nb),
             "samples_note": f"cycle = 50 epochs x {nb} it (SURVEY 8d); excludes the per-sample test-set eval",

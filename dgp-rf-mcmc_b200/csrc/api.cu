@@ -66,15 +66,18 @@ extern "C" int dgprf_version(void) { return 100; }
 
 // ---- workspace layout ------------------------------------------------------------------------
 struct LayerWs {
-    int CS;
+    int CS;        // column splits of the backward (slabs of Dpart / Tpart / Rpart)
+    int CSf;       // column splits of the forward (slabs of Fpart)
+    int tc_cols;   // 0: SIMT forward; 32 | 64: tensor-core forward with that column-tile width
     int64_t n_phi, n_fpart, n_dpart, n_tpart, n_rpart;       // floats per chain
     size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
 };
 struct WsLayout {
     LayerWs L[DGPRF_MAX_LAYERS];
-    int RS;
-    int64_t w_len, h_len, n_dflast;
-    size_t dflast, gwpart, ghyp, llsum, total;
+    int RS;        // row splits of the layered backward (gW slabs)
+    int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
+    int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
+    size_t dflast, gwpart, ghyp, llsum, llpart, gridbar, total;
 };
 
 static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
@@ -118,7 +121,14 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         const dgprf_layer& y = m->layer[l];
         LayerWs& s = w->L[l];
         s.CS = col_splits(y.M);
-        s.n_fpart = (int64_t)s.CS * B * y.g;
+        s.CSf = s.CS;
+        s.tc_cols = 0;
+        if (m->precision == DGPRF_PREC_TF32 && (y.M % 4) == 0 && y.g <= 64) {
+            s.tc_cols = dgprf_tc_tile_cols(B, y.M, m->n_chains);
+            const int t = ceil_div(y.M, s.tc_cols);
+            s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : s.CS;
+        }
+        s.n_fpart = (int64_t)s.CSf * B * y.g;
         s.fpart = take(s.n_fpart);
         if (mode >= DGPRF_MODE_TRAIN) {
             s.n_phi = (int64_t)B * layer_F(y);
@@ -143,7 +153,13 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     if (mode >= DGPRF_MODE_TRAIN) {
         w->n_dflast = (int64_t)B * m->d_out;
         w->dflast = take(w->n_dflast);
-        w->gwpart = take((int64_t)w->RS * w->w_len);
+        w->RSF = dgprf_step_rows_eligible(m, B) ? dgprf_step_rows_groups(B) : 0;
+        w->n_gwpart = (int64_t)(w->RS > w->RSF ? w->RS : w->RSF) * w->w_len;
+        w->gwpart = take(w->n_gwpart);
+        w->n_llpart = w->RSF > 0 ? w->RSF : 1;
+        w->llpart = take(w->n_llpart);
+        w->gridbar = off;                               // two 32-bit words {count, generation}, zero-initialised
+        off += 256;
     }
     if (mode == DGPRF_MODE_HYPER) w->ghyp = take(w->h_len);
     w->total = off;
@@ -183,7 +199,7 @@ static SlabMat fpart_of(const dgprf_model* m, const WsLayout& w, void* ws, int l
     s.cs = w.L[l].n_fpart;
     s.ss = (int64_t)B * m->layer[l].g;
     s.ld = m->layer[l].g;
-    s.n_slabs = w.L[l].CS;
+    s.n_slabs = w.L[l].CSf;
     return s;
 }
 
@@ -195,8 +211,8 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         FwdArgs a;
         memset(&a, 0, sizeof(a));
         a.kind = y.kind; a.B = B; a.d_prev = y.d_prev; a.d_x = y.d_x; a.d = layer_d(y);
-        a.M = y.M; a.g = y.g; a.F = layer_F(y); a.CS = w.L[l].CS; a.ldx = m->d_in; a.do_gemm2 = 1;
-        a.has_mean = y.has_mean;
+        a.M = y.M; a.g = y.g; a.F = layer_F(y); a.CS = w.L[l].CSf; a.ldx = m->d_in; a.do_gemm2 = 1;
+        a.has_mean = y.has_mean; a.tile_cols = w.L[l].tc_cols;
         if (l > 0) a.Fprev = fpart_of(m, w, ws, l - 1, B);
         a.X = X; a.x_cs = x_cs;
         a.z = y.z; a.z_cs = y.z_cs;
@@ -208,7 +224,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
-        const int rc = (m->precision == DGPRF_PREC_TF32 && dgprf_fwd_tc_supported(a))
+        const int rc = (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a))
                            ? dgprf_launch_fwd_tc(a, m->n_chains, st)
                            : dgprf_launch_fwd_simt(a, m->n_chains, st);
         if (rc) return rc;
@@ -291,7 +307,7 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         a.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
         a.h_cs = m->h_cs;
         a.W = m->w_base + y.off_W; a.w_cs = m->w_cs;
-        a.gWpart = wsf(ws, w.gwpart) + y.off_W; a.gw_cs = (int64_t)w.RS * w.w_len; a.gw_ss = w.w_len;
+        a.gWpart = wsf(ws, w.gwpart) + y.off_W; a.gw_cs = w.n_gwpart; a.gw_ss = w.w_len;
         a.Dpart = l > 0 ? wsf(ws, w.L[l].dpart) : nullptr; a.d_cs = w.L[l].n_dpart;
         a.Tpart = hyper ? wsf(ws, w.L[l].tpart) : nullptr; a.t_cs = w.L[l].n_tpart;
         a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
@@ -337,7 +353,7 @@ extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* 
     cudaStream_t st = (cudaStream_t)stream;
     if (gW) {
         DGPRF_REQUIRE(gw_cs >= w.w_len, "gW chain stride %lld < %lld", (long long)gw_cs, (long long)w.w_len);
-        rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), (int64_t)w.RS * w.w_len, w.w_len, w.RS,
+        rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), w.n_gwpart, w.w_len, w.RS,
                                         m->w_base, m->w_cs, prior_inv_N, gW, gw_cs, w.w_len, m->n_chains, st);
         if (rc) return rc;
     }
@@ -352,15 +368,14 @@ extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* 
 }
 
 // ---- update -----------------------------------------------------------------------------------------
-static int update_impl(float* theta, float* mom, int64_t cs, int64_t n, int n_chains,
-                       const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
-                       const dgprf_segment* segs, int n_seg, float lr, float data_size, float beta,
-                       float temperature, int resample, uint64_t seed, uint64_t step, uint32_t stream_base,
-                       const float* eps_inject, const float* mom_inject, cudaStream_t st) {
+static int fill_upd_args(UpdArgs& a, float* theta, float* mom, int64_t cs, int64_t n,
+                         const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
+                         const dgprf_segment* segs, int n_seg, float lr, float data_size, float beta,
+                         float temperature, int resample, uint64_t seed, uint64_t step, uint32_t stream_base,
+                         const float* eps_inject, const float* mom_inject) {
     DGPRF_REQUIRE(theta && mom && grad && segs, "update: NULL buffer");
     DGPRF_REQUIRE(lr > 0.f && data_size > 0.f && beta >= 0.f && beta < 1.f && temperature >= 0.f,
                   "update: need lr>0, N>0, 0<=beta<1, T>=0");
-    UpdArgs a;
     memset(&a, 0, sizeof(a));
     a.theta = theta; a.mom = mom; a.cs = cs; a.n = n;
     a.grad = grad; a.grad_cs = grad_cs; a.n_part = n_part; a.part_stride = part_stride; a.n_seg = n_seg;
@@ -369,6 +384,18 @@ static int update_impl(float* theta, float* mom, int64_t cs, int64_t n, int n_ch
     a.inv_N = 1.f / data_size;
     a.resample = resample; a.seed = seed; a.step = step; a.stream_base = stream_base;
     a.eps_inject = eps_inject; a.mom_inject = mom_inject;
+    return DGPRF_OK;
+}
+
+static int update_impl(float* theta, float* mom, int64_t cs, int64_t n, int n_chains,
+                       const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
+                       const dgprf_segment* segs, int n_seg, float lr, float data_size, float beta,
+                       float temperature, int resample, uint64_t seed, uint64_t step, uint32_t stream_base,
+                       const float* eps_inject, const float* mom_inject, cudaStream_t st) {
+    UpdArgs a;
+    const int rc = fill_upd_args(a, theta, mom, cs, n, grad, grad_cs, n_part, part_stride, segs, n_seg, lr, data_size,
+                                 beta, temperature, resample, seed, step, stream_base, eps_inject, mom_inject);
+    if (rc) return rc;
     return dgprf_launch_update(a, segs, n_seg, n_chains, st);
 }
 
@@ -403,13 +430,36 @@ extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x
     DGPRF_REQUIRE(w_len == w.w_len, "w_len=%lld, layout expects %lld", (long long)w_len, (long long)w.w_len);
     DGPRF_REQUIRE(m->w_cs >= w_len || m->n_chains == 1, "w chain stride too small");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = forward_impl(m, w, X, x_cs, B, mode, ws, nullptr, st);
-    if (rc) return rc;
-    rc = loglik_impl(m, w, Y, y_cs, B, mode, ws, nullptr, nullptr, u_out, 1.f / (float)B, st);
-    if (rc) return rc;
-    rc = backward_impl(m, w, X, x_cs, B, mode, ws, st);
-    if (rc) return rc;
-    rc = update_impl(theta_w, mom_w, m->w_cs, w_len, m->n_chains, wsf(ws, w.gwpart), (int64_t)w.RS * w.w_len, w.RS,
+    int n_part = w.RS;
+    if (!full_bayesian && w.RSF > 0) {
+        // small minibatch: whole forward + likelihood seed + backward in one row-fused kernel, and (when
+        // every CTA is co-resident) the update behind a grid barrier in the same launch
+        UpdArgs ua;
+        rc = fill_upd_args(ua, theta_w, mom_w, m->w_cs, w_len, wsf(ws, w.gwpart), w.n_gwpart, w.RSF, w.w_len, segs_w,
+                           n_seg_w, lr, data_size, momentum_decay, temperature, resample_moments, seed, step, 0u,
+                           eps_w, res_w);
+        if (rc) return rc;
+        ua.n_seg = n_seg_w;
+        bool fused = false;
+        rc = dgprf_launch_step_rows(m, X, x_cs, Y, y_cs, B, wsf(ws, w.gwpart), w.n_gwpart, w.w_len,
+                                    wsf(ws, w.llpart), w.n_llpart, &ua, segs_w, n_seg_w,
+                                    reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.gridbar), u_out, &fused, st);
+        if (rc) return rc;
+        if (fused) return DGPRF_OK;
+        if (u_out) {
+            rc = dgprf_launch_sum_rows(wsf(ws, w.llpart), w.n_llpart, w.RSF, u_out, m->n_chains, st);
+            if (rc) return rc;
+        }
+        n_part = w.RSF;
+    } else {
+        rc = forward_impl(m, w, X, x_cs, B, mode, ws, nullptr, st);
+        if (rc) return rc;
+        rc = loglik_impl(m, w, Y, y_cs, B, mode, ws, nullptr, nullptr, u_out, 1.f / (float)B, st);
+        if (rc) return rc;
+        rc = backward_impl(m, w, X, x_cs, B, mode, ws, st);
+        if (rc) return rc;
+    }
+    rc = update_impl(theta_w, mom_w, m->w_cs, w_len, m->n_chains, wsf(ws, w.gwpart), w.n_gwpart, n_part,
                      w.w_len, segs_w, n_seg_w, lr, data_size, momentum_decay, temperature, resample_moments, seed,
                      step, 0u, eps_w, res_w, st);
     if (rc) return rc;
@@ -421,6 +471,29 @@ extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x
                          eps_h, res_h, st);
         if (rc) return rc;
     }
+    return DGPRF_OK;
+}
+
+extern "C" int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host, const float* Y_host, int y_cols, int B,
+                                      float* X_dev, float* Y_dev, int full_bayesian,
+                                      float* theta_w, float* mom_w, int64_t w_len,
+                                      const dgprf_segment* segs_w, int n_seg_w,
+                                      float* theta_h, float* mom_h, int64_t h_len,
+                                      const dgprf_segment* segs_h, int n_seg_h,
+                                      float lr, float data_size, float momentum_decay, float temperature,
+                                      int resample_moments, uint64_t seed, uint64_t step,
+                                      void* ws, size_t ws_bytes, float* u_dev, float* u_host, void* stream) {
+    DGPRF_REQUIRE(m && X_host && Y_host && X_dev && Y_dev && B >= 1 && y_cols >= 1, "step_host: bad arguments");
+    DGPRF_REQUIRE(u_host == nullptr || u_dev != nullptr, "step_host: u_host needs the u_dev staging word");
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPRF_CHECK_CUDA(cudaMemcpyAsync(X_dev, X_host, sizeof(float) * (size_t)B * m->d_in, cudaMemcpyHostToDevice, st));
+    DGPRF_CHECK_CUDA(cudaMemcpyAsync(Y_dev, Y_host, sizeof(float) * (size_t)B * y_cols, cudaMemcpyHostToDevice, st));
+    const int rc = dgprf_sgmcmc_step(m, X_dev, 0, Y_dev, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,
+                                     theta_h, mom_h, h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature,
+                                     resample_moments, seed, step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes,
+                                     u_host ? u_dev : nullptr, stream);
+    if (rc) return rc;
+    if (u_host) DGPRF_CHECK_CUDA(cudaMemcpyAsync(u_host, u_dev, sizeof(float) * m->n_chains, cudaMemcpyDeviceToHost, st));
     return DGPRF_OK;
 }
 

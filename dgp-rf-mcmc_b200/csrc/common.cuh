@@ -41,7 +41,8 @@ static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m)
 constexpr int kTM = 64;        // batch rows per tile
 constexpr int kTN = 64;        // random-feature columns per tile
 constexpr int kKC = 32;        // K chunk of GEMM #1 (input width)
-constexpr int kMaxCS = 8;      // column splits  -> partial slabs of F / dF_prev
+constexpr int kMaxCS = 8;      // column splits of the SIMT kernels -> partial slabs of F / dF_prev
+constexpr int kMaxSlabs = 16;  // most slabs any producer writes (tensor-core forward with 32-wide tiles)
 constexpr int kMaxRS = 16;     // row splits     -> partial slabs of gW
 constexpr int kThreads = 256;
 
@@ -60,20 +61,20 @@ struct SlabMat {
     int32_t n_slabs;
 };
 
-// All slab loads are issued before the (fixed-order) adds so they overlap: n_slabs <= kMaxCS.
+// All slab loads are issued before the (fixed-order) adds so they overlap: n_slabs <= kMaxSlabs.
 __device__ __forceinline__ float slab_load(const SlabMat& m, int chain, int64_t row, int col) {
     const float* p = m.ptr + chain * m.cs + row * m.ld + col;
-    float t[kMaxCS];
+    float t[kMaxSlabs];
 #pragma unroll
-    for (int s = 0; s < kMaxCS; ++s) t[s] = s < m.n_slabs ? __ldg(p + s * m.ss) : 0.f;
+    for (int s = 0; s < kMaxSlabs; ++s) t[s] = s < m.n_slabs ? __ldg(p + s * m.ss) : 0.f;
     float v = t[0];
 #pragma unroll
-    for (int s = 1; s < kMaxCS; ++s) v += t[s];
+    for (int s = 1; s < kMaxSlabs; ++s) v += t[s];
     return v;
 }
 
 struct FwdArgs {
-    int32_t kind, B, d_prev, d_x, d, M, g, F, CS, ldx, do_gemm2, has_mean;
+    int32_t kind, B, d_prev, d_x, d, M, g, F, CS, ldx, do_gemm2, has_mean, tile_cols;
     SlabMat Fprev;                       // previous GP-layer output (partial slabs), ld = d_prev
     const float* X;  int64_t x_cs;       // model input, ld = ldx
     const float* z;  int64_t z_cs;       // [d, M]

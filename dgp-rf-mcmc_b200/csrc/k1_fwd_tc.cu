@@ -16,23 +16,26 @@
 #include "tc_common.cuh"
 
 constexpr int TC_BM = 128;       // UMMA M
-constexpr int TC_BN = 64;        // random-feature columns per tile (UMMA N of GEMM #1)
 constexpr int TC_KG = 2;         // 32-wide K blocks of GEMM #1 staged per group (hi and lo copies of each)
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BLK = TC_BM * 128;   // bytes of one [128 x 32 tf32] block
-constexpr int TC_B_BLK = TC_BN * 128;
-constexpr uint32_t TC_TMEM_COLS = 128;  // D1: 64 columns, D2: up to 64 columns
+constexpr uint32_t TC_TMEM_COLS = 128;  // D1: BN (<= 64) columns, D2: up to 64 columns
 
-template <int NG>
+// NG: padded n_gp (UMMA N of GEMM #2).  BN: random-feature columns per tile (UMMA N of GEMM #1):
+// 64 for large problems, 32 when the grid would otherwise leave most SMs idle.
+template <int NG, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA1 = sm;                                 // [hi blocks 0..KG) | lo blocks 0..KG)]
+    constexpr int TC_BN = BN;
+    constexpr int TC_B_BLK = BN * 128;
+    constexpr int NPB = BN / 32;                       // 32-wide Phi blocks per half (cos | sin)
     uint8_t* sB1 = sA1 + 2 * TC_KG * TC_A_BLK;         // same split
-    uint8_t* sPhi = sB1 + 2 * TC_KG * TC_B_BLK;        // 4 blocks: cos 0,1 | sin 2,3  (ARC: 0,1)
-    uint8_t* sW = sPhi + 4 * TC_A_BLK;                 // 4 blocks of [NG x 128 B]
-    float* bias_s = reinterpret_cast<float*>(sW + 4 * NG * 128);
+    uint8_t* sPhi = sB1 + 2 * TC_KG * TC_B_BLK;        // 2*NPB blocks: cos 0..NPB) | sin NPB..2NPB)  (ARC: cos only)
+    uint8_t* sW = sPhi + 2 * NPB * TC_A_BLK;           // 2*NPB blocks of [NG x 128 B]
+    float* bias_s = reinterpret_cast<float*>(sW + 2 * NPB * NG * 128);
     uint64_t* bar = reinterpret_cast<uint64_t*>(bias_s + TC_BM);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -65,7 +68,7 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
     const int n_kb = (a.d + 31) / 32;                    // 32-wide K blocks of GEMM #1
     const int n_kg = (n_kb + TC_KG - 1) / TC_KG;
     const bool a_resident = n_kg == 1;                   // the whole A operand stays in shared memory
-    const int nb2 = rbf ? 4 : 2;                         // 32-wide K blocks of GEMM #2 per column tile
+    const int nb2 = rbf ? 2 * NPB : NPB;                 // 32-wide K blocks of GEMM #2 per column tile
     bool d2_started = false;
 
     const int n_ct = (a.M + TC_BN - 1) / TC_BN;
@@ -80,60 +83,83 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
             const int nblk = min(TC_KG, n_kb - kg * TC_KG);
             // ---- stage A = tf32(in * s): lanes along K (coalesced rows of X / F_prev) ----
             if (!a_resident || ct == cs) {
-                for (int kbl = 0; kbl < nblk; ++kbl) {
+                float v[TC_KG][TC_BM / 8], sq[TC_KG], mq[TC_KG];
+#pragma unroll
+                for (int kbl = 0; kbl < TC_KG; ++kbl) {          // every load of the group is issued first
                     const int q = (kg * TC_KG + kbl) * 32 + lane;
-                    const bool qok = q < a.d;
-                    const float sq = qok ? expf(__ldg(ls + q)) : 0.f;
-                    const float mq = (qok && mean) ? __ldg(mean + q) : 0.f;
-                    float v[TC_BM / 8];
+                    const bool qok = kbl < nblk && q < a.d;
+                    sq[kbl] = qok ? expf(__ldg(ls + q)) : 0.f;
+                    mq[kbl] = (qok && mean) ? __ldg(mean + q) : 0.f;
 #pragma unroll
                     for (int rr = 0; rr < TC_BM / 8; ++rr) {
                         const int64_t row = row0 + warp + 8 * rr;
                         float t = 0.f;
                         if (row < a.B && qok)
                             t = q < a.d_prev ? slab_load(a.Fprev, chain, row, q) : __ldg(X + row * a.ldx + (q - a.d_prev));
-                        v[rr] = t;
+                        v[kbl][rr] = t;
                     }
+                }
 #pragma unroll
-                    for (int rr = 0; rr < TC_BM / 8; ++rr) {
-                        const int r = warp + 8 * rr;
-                        const float x = v[rr] * sq, hi = tc::to_tf32(x);
-                        *reinterpret_cast<float*>(sA1 + kbl * TC_A_BLK + tc::sw128_off(r, lane)) = hi;
-                        *reinterpret_cast<float*>(sA1 + (TC_KG + kbl) * TC_A_BLK + tc::sw128_off(r, lane)) = tc::to_tf32(x - hi);
-                        bsum[rr] = fmaf(v[rr], mq, bsum[rr]);
+                for (int kbl = 0; kbl < TC_KG; ++kbl) {
+                    if (kbl < nblk) {
+#pragma unroll
+                        for (int rr = 0; rr < TC_BM / 8; ++rr) {
+                            const int r = warp + 8 * rr;
+                            const float x = v[kbl][rr] * sq[kbl], hi = tc::to_tf32(x);
+                            *reinterpret_cast<float*>(sA1 + kbl * TC_A_BLK + tc::sw128_off(r, lane)) = hi;
+                            *reinterpret_cast<float*>(sA1 + (TC_KG + kbl) * TC_A_BLK + tc::sw128_off(r, lane)) = tc::to_tf32(x - hi);
+                            bsum[rr] = fmaf(v[kbl][rr], mq[kbl], bsum[rr]);
+                        }
                     }
                 }
             }
             // ---- stage B = tf32(z tile), rows = feature columns, 16-byte chunks along K ----
-            for (int kbl = 0; kbl < nblk; ++kbl) {
-                const int kb = kg * TC_KG + kbl;
+            {
+                constexpr int NU = TC_KG * TC_BN * 8 / TC_THREADS;        // (block, row, chunk) items per thread
+                float zx[NU][4];
 #pragma unroll
-                for (int u = 0; u < TC_BN * 8 / TC_THREADS; ++u) {
+                for (int u = 0; u < NU; ++u) {
                     const int e = tid + u * TC_THREADS;
-                    const int n = e % TC_BN, ch = e / TC_BN;
+                    const int n = e % TC_BN, ch = (e / TC_BN) & 7, kbl = e / (TC_BN * 8);
                     const int col = c0 + n;
-                    float4 o, ol;
-                    float* of = reinterpret_cast<float*>(&o);
-                    float* olf = reinterpret_cast<float*>(&ol);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int q = kb * 32 + ch * 4 + i;
-                        const float x = (q < a.d && col < a.M) ? __ldg(z + (int64_t)q * a.M + col) : 0.f;
-                        of[i] = tc::to_tf32(x);
-                        olf[i] = tc::to_tf32(x - of[i]);
+                        const int q = (kg * TC_KG + kbl) * 32 + ch * 4 + i;
+                        zx[u][i] = (kbl < nblk && q < a.d && col < a.M) ? __ldg(z + (int64_t)q * a.M + col) : 0.f;
                     }
-                    *reinterpret_cast<float4*>(sB1 + kbl * TC_B_BLK + tc::sw128_chunk(n, ch)) = o;
-                    *reinterpret_cast<float4*>(sB1 + (TC_KG + kbl) * TC_B_BLK + tc::sw128_chunk(n, ch)) = ol;
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int e = tid + u * TC_THREADS;
+                    const int n = e % TC_BN, ch = (e / TC_BN) & 7, kbl = e / (TC_BN * 8);
+                    if (kbl < nblk) {
+                        float4 o, ol;
+                        o.x = tc::to_tf32(zx[u][0]); o.y = tc::to_tf32(zx[u][1]); o.z = tc::to_tf32(zx[u][2]); o.w = tc::to_tf32(zx[u][3]);
+                        ol.x = tc::to_tf32(zx[u][0] - o.x); ol.y = tc::to_tf32(zx[u][1] - o.y);
+                        ol.z = tc::to_tf32(zx[u][2] - o.z); ol.w = tc::to_tf32(zx[u][3] - o.w);
+                        *reinterpret_cast<float4*>(sB1 + kbl * TC_B_BLK + tc::sw128_chunk(n, ch)) = o;
+                        *reinterpret_cast<float4*>(sB1 + (TC_KG + kbl) * TC_B_BLK + tc::sw128_chunk(n, ch)) = ol;
+                    }
                 }
             }
             // ---- stage the W tile of GEMM #2 once per column tile ----
             if (kg == 0 && a.do_gemm2) {
-                for (int e = tid; e < nb2 * 32 * NG; e += TC_THREADS) {
+                constexpr int NW = 2 * BN * NG / TC_THREADS;             // W elements per thread (both halves)
+                float wv[NW];
+#pragma unroll
+                for (int u = 0; u < NW; ++u) {
+                    const int e = tid + u * TC_THREADS;
+                    const int j = e % NG, kf = e / NG;                  // kf in [0, 2*BN): cos half | sin half
+                    const int col = c0 + (kf % BN);
+                    const int64_t frow = (kf >= BN ? a.M : 0) + col;
+                    wv[u] = (j < a.g && col < a.M && (rbf || kf < BN)) ? __ldg(W + frow * a.g + j) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < NW; ++u) {
+                    const int e = tid + u * TC_THREADS;
                     const int j = e % NG, kf = e / NG;
-                    const int col = c0 + (kf & 63);
-                    const int64_t frow = (kf >= 64 ? a.M : 0) + col;
-                    const float v = (j < a.g && col < a.M) ? tc::to_tf32(__ldg(W + frow * a.g + j)) : 0.f;
-                    *reinterpret_cast<float*>(sW + (kf >> 5) * (NG * 128) + tc::sw128_off(j, kf & 31)) = v;
+                    if (rbf || kf < BN)
+                        *reinterpret_cast<float*>(sW + (kf >> 5) * (NG * 128) + tc::sw128_off(j, kf & 31)) = tc::to_tf32(wv[u]);
                 }
             }
             if (a.has_mean && kg == n_kg - 1 && (!a_resident || ct == cs)) {
@@ -169,20 +195,22 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
 
         // ---- epilogue: TMEM -> registers -> activation -> swizzled shared tile ----
         {
+            constexpr int CW = BN / 2;                           // columns per warp: 32 (BN=64) | 16 (BN=32)
             const int lq = warp & 3, chh = warp >> 2;            // TMEM lane quarter, column half
             const int r = 32 * lq + lane;
-            float p[32];
-            tc::tmem_ld32(tmem_d1 + ((uint32_t)(32 * lq) << 16) + 32 * chh, p);
+            float p[CW];
+            if constexpr (CW == 32) tc::tmem_ld32(tmem_d1 + ((uint32_t)(32 * lq) << 16) + CW * chh, p);
+            else tc::tmem_ld16(tmem_d1 + ((uint32_t)(32 * lq) << 16) + CW * chh, p);
             tc::tmem_ld_wait();
             const float bias = a.has_mean ? bias_s[r] : 0.f;
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
                 float4 f0, f1;
                 float* f0p = reinterpret_cast<float*>(&f0);
                 float* f1p = reinterpret_cast<float*>(&f1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const bool live = (c0 + 32 * chh + 4 * c4 + i) < a.M;
+                    const bool live = (c0 + CW * chh + 4 * c4 + i) < a.M;
                     const float x = p[4 * c4 + i] + bias;
                     if (rbf) {
                         float s, c;
@@ -194,8 +222,10 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
                         f1p[i] = 0.f;
                     }
                 }
-                *reinterpret_cast<float4*>(sPhi + chh * TC_A_BLK + tc::sw128_chunk(r, c4)) = f0;
-                if (rbf) *reinterpret_cast<float4*>(sPhi + (2 + chh) * TC_A_BLK + tc::sw128_chunk(r, c4)) = f1;
+                // column CW*chh + 4*c4 of the tile -> 32-wide block and 16-byte chunk inside it
+                const int cb = (CW * chh + 4 * c4) >> 5, cc = ((CW * chh + 4 * c4) & 31) >> 2;
+                *reinterpret_cast<float4*>(sPhi + cb * TC_A_BLK + tc::sw128_chunk(r, cc)) = f0;
+                if (rbf) *reinterpret_cast<float4*>(sPhi + (NPB + cb) * TC_A_BLK + tc::sw128_chunk(r, cc)) = f1;
             }
         }
         tc::tc_fence_before();
@@ -213,10 +243,10 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
                 tc::umma_commit(bar);
             }
             if (a.Phi != nullptr) {                              // saved features for the backward
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < NPB; ++b) {
                     if (c0 + 32 * b >= a.M) break;
                     tc::tma_store_3d(&map_cos, tc::smem_u32(sPhi + b * TC_A_BLK), c0 + 32 * b, row0, chain);
-                    if (rbf) tc::tma_store_3d(&map_sin, tc::smem_u32(sPhi + (2 + b) * TC_A_BLK), c0 + 32 * b, row0, chain);
+                    if (rbf) tc::tma_store_3d(&map_sin, tc::smem_u32(sPhi + (NPB + b) * TC_A_BLK), c0 + 32 * b, row0, chain);
                 }
                 tc::tma_commit();
             }
@@ -252,17 +282,17 @@ k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
     if (warp == 0) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
-static size_t tc_fwd_smem_bytes(int NG) {
-    return 1024 + 2 * (size_t)TC_KG * TC_A_BLK + 2 * (size_t)TC_KG * TC_B_BLK + 4 * (size_t)TC_A_BLK + 4 * (size_t)NG * 128 +
-           TC_BM * sizeof(float) + 16;
+static size_t tc_fwd_smem_bytes(int NG, int BN) {
+    return 1024 + 2 * (size_t)TC_KG * TC_A_BLK + 2 * (size_t)TC_KG * BN * 128 + 2 * (size_t)(BN / 32) * TC_A_BLK +
+           2 * (size_t)(BN / 32) * NG * 128 + TC_BM * sizeof(float) + 16;
 }
 
-template <int NG>
+template <int NG, int BN>
 static int launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st) {
-    const size_t smem = tc_fwd_smem_bytes(NG);
+    const size_t smem = tc_fwd_smem_bytes(NG, BN);
     static bool configured = false;
     if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc<NG, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     CUtensorMap mc, ms;
@@ -277,7 +307,7 @@ static int launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st) {
         }
     }
     dim3 grid(ceil_div(a.B, TC_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc", st); k1_fwd_tc<NG><<<grid, TC_THREADS, smem, st>>>(a, mc, ms); }
+    { ProfScope _ps("k1_fwd_tc", st); k1_fwd_tc<NG, BN><<<grid, TC_THREADS, smem, st>>>(a, mc, ms); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -287,9 +317,21 @@ bool dgprf_fwd_tc_supported(const FwdArgs& a) {
     return (a.M % 4 == 0) && a.g <= 64 && (a.Phi == nullptr || (a.phi_cs % 4) == 0);
 }
 
+// Column-tile width of the tensor-core kernels for a layer: 32 when 64-wide tiles would leave most of the
+// 148 SMs without a CTA (small minibatches), else 64.  The workspace layout (api.cu) uses the same rule.
+int dgprf_tc_tile_cols(int B, int M, int n_chains) {
+    const int64_t ctas64 = (int64_t)ceil_div(B, TC_BM) * (ceil_div(M, 64) < kMaxCS ? ceil_div(M, 64) : kMaxCS) * n_chains;
+    return ctas64 < 120 ? 32 : 64;
+}
+
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const int g = a.do_gemm2 ? a.g : 1;
-    if (g <= 16) return launch_fwd_tc<16>(a, n_chains, st);
-    if (g <= 32) return launch_fwd_tc<32>(a, n_chains, st);
-    return launch_fwd_tc<64>(a, n_chains, st);
+    if (a.tile_cols == 32) {
+        if (g <= 16) return launch_fwd_tc<16, 32>(a, n_chains, st);
+        if (g <= 32) return launch_fwd_tc<32, 32>(a, n_chains, st);
+        return launch_fwd_tc<64, 32>(a, n_chains, st);
+    }
+    if (g <= 16) return launch_fwd_tc<16, 64>(a, n_chains, st);
+    if (g <= 32) return launch_fwd_tc<32, 64>(a, n_chains, st);
+    return launch_fwd_tc<64, 64>(a, n_chains, st);
 }

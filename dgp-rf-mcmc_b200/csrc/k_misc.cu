@@ -20,6 +20,21 @@ int dgprf_launch_sum_slabs(const SlabMat& m, int B, int ncol, float* out, int64_
     return DGPRF_OK;
 }
 
+// ---- out[c] = sum_i in[c][i] (fixed order; one CTA per chain) ---------------------------------
+__global__ void __launch_bounds__(256) k_sum_rows(const float* in, int64_t in_cs, int n, float* out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += in[blockIdx.x * in_cs + i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+int dgprf_launch_sum_rows(const float* in, int64_t in_cs, int n, float* out, int n_chains, cudaStream_t st) {
+    k_sum_rows<<<n_chains, 256, 0, st>>>(in, in_cs, n, out);
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}
+
 // ---- gradient finalisation: out = sum_p part_p (+ theta * inv_N) ---------------------------
 __global__ void k_grad_finalize(const float* part, int64_t part_cs, int64_t part_ss, int n_part,
                                 const float* theta, int64_t theta_cs, float inv_N,

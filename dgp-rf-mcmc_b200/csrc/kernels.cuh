@@ -39,6 +39,7 @@ struct HypArgs {
 
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_fwd_tc_supported(const FwdArgs& a);
+int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_bwd_simt(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st);
@@ -48,3 +49,13 @@ int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_
                                const float* theta, int64_t theta_cs, float inv_N,
                                float* out, int64_t out_cs, int64_t n, int n_chains, cudaStream_t st);
 int dgprf_launch_hyper_reduce(const HypArgs& a, int n_chains, cudaStream_t st);
+
+// row-fused step (k9_step_rows.cu)
+size_t dgprf_step_rows_smem(const dgprf_model* m);
+int dgprf_step_rows_groups(int B);
+bool dgprf_step_rows_eligible(const dgprf_model* m, int B);
+int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B,
+                           float* gwpart, int64_t gw_cs, int64_t gw_ss, float* ll_part, int64_t ll_cs,
+                           const UpdArgs* upd, const dgprf_segment* segs, int n_seg, unsigned int* bar, float* u_out,
+                           bool* fused, cudaStream_t st);
+int dgprf_launch_sum_rows(const float* in, int64_t in_cs, int n, float* out, int n_chains, cudaStream_t st);

@@ -115,6 +115,7 @@ class Engine:
             z = [torch.randn(zc, s.d, s.M, **f32) for s in spec.layers]
         self.z = z
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._staging: Dict = {}
         self._model = None
         self._scratch = torch.zeros(max(4, self.C), **f32)
         # segment tables: name -> (offset, length, mass, flags)
@@ -169,6 +170,8 @@ class Engine:
     def set_precision(self, name: str):
         self.precision = {"fp32": _ffi.PREC_FP32, "tf32": _ffi.PREC_TF32}[name]
         self._model = None
+        self._ws.clear()            # the workspace layout depends on the precision mode
+        self._staging.clear()
 
     def set_mass(self, name: str, mass: float):
         (self.seg_w if name in self.seg_w else self.seg_h)[name][2] = float(mass)
@@ -320,6 +323,32 @@ class Engine:
             float(lr), float(data_size), float(momentum_decay), float(temperature), int(bool(resample)),
             int(seed), int(step), p(eps_w), p(res_w), p(eps_h), p(res_h),
             ws.data_ptr(), ws.numel(), p(u_out), _ffi.stream_ptr()))
+
+    def step_host(self, X_host: torch.Tensor, Y_host: torch.Tensor, data_size: float, lr: float, momentum_decay: float,
+                  temperature: float, resample: bool, full_bayesian: bool, seed: int, step: int,
+                  u_host: Optional[torch.Tensor] = None):
+        """sgmcmc_update from a HOST minibatch (fp32 contiguous CPU tensors, ideally pinned): the H2D copies,
+        the step and the optional D2H read of sum_i ll_i are enqueued by ONE C call; nothing synchronises."""
+        m = self.model()
+        B, dx = X_host.shape
+        yc = Y_host.shape[1]
+        assert dx == self.spec.d_in and Y_host.shape[0] == B and self.C == 1
+        key = (B, yc, bool(full_bayesian))
+        st = self._staging.get(key)
+        if st is None:
+            mode = _ffi.MODE_HYPER if full_bayesian else _ffi.MODE_TRAIN
+            st = (torch.empty(B, dx, device=self.device), torch.empty(B, yc, device=self.device),
+                  torch.zeros(max(1, self.C), device=self.device), self.workspace(m, B, mode))
+            self._staging[key] = st
+        ws = st[3]
+        sw, nsw, sh, nsh = self._segments()
+        _ffi.check(_ffi.lib().dgprf_sgmcmc_step_host(
+            C.byref(m), X_host.data_ptr(), Y_host.data_ptr(), yc, B, st[0].data_ptr(), st[1].data_ptr(),
+            int(full_bayesian), self.theta_w.data_ptr(), self.mom_w.data_ptr(), self.layout.w_len, sw, nsw,
+            self.theta_h.data_ptr(), self.mom_h.data_ptr(), self.layout.h_len, sh, nsh,
+            float(lr), float(data_size), float(momentum_decay), float(temperature), int(bool(resample)),
+            int(seed), int(step), ws.data_ptr(), ws.numel(), st[2].data_ptr(),
+            u_host.data_ptr() if u_host is not None else None, _ffi.stream_ptr()))
 
     def log_prior(self, t: torch.Tensor) -> torch.Tensor:
         """sum log N(t; 0, 1) over a contiguous tensor -> scalar tensor (models/dgp.py:129-136)."""

@@ -126,6 +126,7 @@ class DGP_RF:
         self.BNN._engine_owner = self
         self._seed = int.from_bytes(os.urandom(7), "little")
         self._step = 0
+        self._sampler_ready = {}
 
     # hooks used by Variable.moments / Variable.M
     def _moment_view(self, var):
@@ -237,15 +238,26 @@ class DGP_RF:
 
     # ---- SG-MCMC (dgp.py:184-216) ---------------------------------------------------------------------
     def sgmcmc_update(self, X_batch, Y_batch, data_size, lr=0.01, momentum_decay=0.95,
-                      resample_moments=False, temperature=1., full_bayesian=False, *, eps=None, resample=None):
+                      resample_moments=False, temperature=1., full_bayesian=False, *, eps=None, resample=None,
+                      u_host=None):
         """One SGHMC step (SGLD when momentum_decay == 0) on W (and on every trainable
         hyper-parameter when full_bayesian)."""
-        watched = self.trainable_variables if full_bayesian else self.W_mcmc
-        for param in watched:
-            assert hasattr(param, "moments"), "Trainable Params do not have attr moments!"
-            assert hasattr(param, "M"), "Trainable Params do not have attr preconditioner M!"
+        if not self._sampler_ready.get(bool(full_bayesian), False):       # checked once, then cached
+            watched = self.trainable_variables if full_bayesian else self.W_mcmc
+            for param in watched:
+                assert param._mom is not None, "Trainable Params do not have attr moments!"
+                assert param._M is not None, "Trainable Params do not have attr preconditioner M!"
+            self._sampler_ready[bool(full_bayesian)] = True
         e = self._engine
         self._step += 1
+        if (eps is None and resample is None and torch.is_tensor(X_batch) and torch.is_tensor(Y_batch)
+                and X_batch.device.type == "cpu" and X_batch.dtype == torch.float32 and Y_batch.dtype == torch.float32
+                and X_batch.ndim == 2 and Y_batch.ndim == 2 and X_batch.is_contiguous() and Y_batch.is_contiguous()
+                and e.device.type == "cuda"):
+            # host minibatch: H2D copies + step enqueued by one C call (dgprf_sgmcmc_step_host)
+            e.step_host(X_batch, Y_batch, float(data_size), float(lr), float(momentum_decay), float(temperature),
+                        bool(resample_moments), bool(full_bayesian), self._seed, self._step, u_host=u_host)
+            return
         inj = {}
         if eps is not None:
             inj["eps_w"] = e.flat_from_named(eps, "w")

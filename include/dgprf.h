@@ -166,6 +166,21 @@ int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x_cs, const 
                       const float* eps_w, const float* res_w, const float* eps_h, const float* res_h,
                       void* ws, size_t ws_bytes, float* u_out, void* stream);
 
+/* The same step driven from HOST minibatches (the reference's drivers hand numpy / tf.data batches to
+ * sgmcmc_update, experiments/utils_training.py:45-61): X_host [B, d_in] and Y_host [B, d_out | 1] are copied
+ * to the caller's device staging buffers X_dev / Y_dev with cudaMemcpyAsync on `stream` (pinned host memory
+ * makes them truly asynchronous), the step runs, and sum_i ll_i is copied back to u_host (nullable; u_dev is
+ * its device staging word).  One chain-shared minibatch (x_cs = y_cs = 0).  Nothing synchronises. */
+int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host, const float* Y_host, int y_cols, int B,
+                           float* X_dev, float* Y_dev, int full_bayesian,
+                           float* theta_w, float* mom_w, int64_t w_len,
+                           const dgprf_segment* segs_w, int n_seg_w,
+                           float* theta_h, float* mom_h, int64_t h_len,
+                           const dgprf_segment* segs_h, int n_seg_h,
+                           float lr, float data_size, float momentum_decay, float temperature,
+                           int resample_moments, uint64_t seed, uint64_t step,
+                           void* ws, size_t ws_bytes, float* u_dev, float* u_host, void* stream);
+
 /* ---- reductions ------------------------------------------------------------------------ */
 /* sum_i log N(x_i; 0, 1) over [C][n] -> out[C]  (prior_W, models/dgp.py:129-136; the
  * per-variable reduce_sum(log_gaussian) of :144-146,156,179-180). */

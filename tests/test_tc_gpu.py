@@ -83,8 +83,10 @@ def test_tc_saved_features_and_gradients(name):
     ws = e.workspace(m, X.shape[0], _ffi.MODE_TRAIN)
     # layer-0 Phi sits right after layer-0's F partial slabs in the workspace (csrc/api.cu make_layout)
     s0 = e.spec.layers[0]
-    CS = min((s0.M + 63) // 64, 8)
-    off = ((CS * X.shape[0] * s0.g * 4 + 255) // 256) * 256
+    Bn = X.shape[0]
+    ctas64 = ((Bn + 127) // 128) * min((s0.M + 63) // 64, 8)
+    CS = min((s0.M + 31) // 32, 16) if ctas64 < 120 else min((s0.M + 63) // 64, 8)   # dgprf_tc_tile_cols
+    off = ((CS * Bn * s0.g * 4 + 255) // 256) * 256
     Phi0 = ws[off:off + X.shape[0] * s0.F * 4].view(torch.float32).view(X.shape[0], s0.F)
     assert rel_err(Phi0, Phis[0]) < 1e-4
 
