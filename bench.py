@@ -157,6 +157,7 @@ def run_ours(args, rank, world):
 
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
     local = int(os.environ.get("LOCAL_RANK", 0))
