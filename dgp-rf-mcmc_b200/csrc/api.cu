@@ -311,7 +311,9 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         a.Dpart = l > 0 ? wsf(ws, w.L[l].dpart) : nullptr; a.d_cs = w.L[l].n_dpart;
         a.Tpart = hyper ? wsf(ws, w.L[l].tpart) : nullptr; a.t_cs = w.L[l].n_tpart;
         a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
-        int rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
+        int rc = (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc_supported(a))
+                     ? dgprf_launch_bwd_tc(a, m->n_chains, st)
+                     : dgprf_launch_bwd_simt(a, m->n_chains, st);
         if (rc) return rc;
         if (hyper) {
             HypArgs h;

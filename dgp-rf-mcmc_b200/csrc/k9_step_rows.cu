@@ -488,7 +488,7 @@ int dgprf_step_rows_groups(int B) { return ceil_div(B, kSR); }
 // minibatch is small enough that one CTA per 8 rows is a sensible grid.
 bool dgprf_step_rows_eligible(const dgprf_model* m, int B) {
     if (m->precision != DGPRF_PREC_FP32) return false;
-    if ((int64_t)ceil_div(B, kSR) * m->n_chains > 148 * 8) return false;
+    if ((int64_t)ceil_div(B, kSR) * m->n_chains > 160) return false;      // more than ~one wave: the layered kernels win
     for (int l = 0; l < m->n_layers; ++l)
         if (m->layer[l].g > kSN || m->layer[l].d_prev > kSN) return false;
     return dgprf_step_rows_smem(m) <= 220 * 1024;

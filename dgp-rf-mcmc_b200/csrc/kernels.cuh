@@ -41,6 +41,8 @@ int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_fwd_tc_supported(const FwdArgs& a);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
+bool dgprf_bwd_tc_supported(const BwdArgs& a);
+int dgprf_launch_bwd_tc(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_bwd_simt(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, int n_chains, cudaStream_t st);

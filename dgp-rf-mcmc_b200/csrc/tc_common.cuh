@@ -19,6 +19,17 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
 // byte offset of 16-byte chunk c (0..7) of row r
 __device__ __forceinline__ uint32_t sw128_chunk(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// ---- 128-byte swizzle with a 32-byte atom (Swizzle<2,5,2>): the only layout tcgen05 accepts for MN-major
+// tf32 operands (UMMA SWIZZLE_128B_BASE32B == TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Rows are 128 B,
+// the 32-byte unit u of row r is stored at unit position u ^ (r & 3); the pattern repeats every 4 rows.
+__device__ __forceinline__ uint32_t sw128b32_off(int r, int k) {
+    return (uint32_t)(r * 128 + ((((k >> 3) ^ (r & 3)) << 5) | ((k & 7) << 2)));
+}
+// byte offset of 16-byte chunk c (0..7) of row r in that layout
+__device__ __forceinline__ uint32_t sw128b32_chunk(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -128,4 +139,5 @@ __device__ __forceinline__ void tma_wait0() { asm volatile("cp.async.bulk.wait_g
 // Host: 3-D tensor map {cols (inner), rows, chains} of an fp32 matrix view, box {32, box_rows, 1},
 // SWIZZLE_128B.  Returns 0 on success (message in dgprf_last_error otherwise).
 int dgprf_make_tmap_3d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t chains,
-                       uint64_t row_stride_floats, uint64_t chain_stride_floats, uint32_t box_rows);
+                       uint64_t row_stride_floats, uint64_t chain_stride_floats, uint32_t box_rows,
+                       bool atom32 = false);      // atom32: SWIZZLE_128B_ATOM_32B (MN-major tf32 UMMA operands)

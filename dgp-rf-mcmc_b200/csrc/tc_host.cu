@@ -21,7 +21,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int dgprf_make_tmap_3d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t chains,
-                       uint64_t row_stride_floats, uint64_t chain_stride_floats, uint32_t box_rows) {
+                       uint64_t row_stride_floats, uint64_t chain_stride_floats, uint32_t box_rows, bool atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         dgprf_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -37,7 +37,9 @@ int dgprf_make_tmap_3d(CUtensorMap* map, const float* base, uint64_t cols, uint6
     const cuuint32_t box[3] = {32, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         dgprf_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
