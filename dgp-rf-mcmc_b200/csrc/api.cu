@@ -77,7 +77,7 @@ struct WsLayout {
     int RS;        // row splits of the layered backward (gW slabs)
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
-    size_t dflast, gwpart, ghyp, llsum, llpart, gridbar, total;
+    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, total;
 };
 
 static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
@@ -150,6 +150,7 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     w->w_len = round_up(w->w_len, 4);
     w->h_len = round_up(w->h_len, 4);
     w->llsum = take(1);
+    w->likpart = take(2 * 64);
     if (mode >= DGPRF_MODE_TRAIN) {
         w->n_dflast = (int64_t)B * m->d_out;
         w->dflast = take(w->n_dflast);
@@ -258,6 +259,7 @@ static int loglik_impl(const dgprf_model* m, const WsLayout& w, const float* Y, 
     a.h_cs = m->h_cs;
     a.ll_rows = ll_rows; a.aux_rows = aux_rows;
     a.ll_sum = ll_sum ? ll_sum : wsf(ws, w.llsum);
+    a.part = wsf(ws, w.likpart);
     a.inv_B = inv_B;
     if (inv_B > 0.f) {
         DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "dU/dF needs a TRAIN/HYPER workspace");

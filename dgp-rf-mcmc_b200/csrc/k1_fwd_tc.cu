@@ -27,7 +27,9 @@ template <int NG, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k1_fwd_tc(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by offsetting the shared array itself: the pointer keeps its shared-memory address
+    // space (a round trip through uintptr_t makes every access a generic LD/ST)
+    uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA1 = sm;                                 // [hi blocks 0..KG) | lo blocks 0..KG)]
     constexpr int TC_BN = BN;
     constexpr int TC_B_BLK = BN * 128;

@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 k2_bwd_tc(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int KGB = NG / 32;
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by offsetting the shared array itself: the pointer keeps its shared-memory address
+    // space (a round trip through uintptr_t makes every access a generic LD/ST)
+    uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sPhi = sm;                              // 4 blocks: cos 0,1 | sin 2,3
     uint8_t* sdF = sPhi + 4 * BT_BLK;                // KGB blocks [128 rows x 32 j]  K-major, 16-byte-atom swizzle
     uint8_t* sdF2 = sdF + KGB * BT_BLK;              // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)

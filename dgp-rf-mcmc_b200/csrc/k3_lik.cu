@@ -4,7 +4,8 @@
 // plus what the evaluation methods derive from the same pass
 //   models/regression_model.py:46   se = mean_D (y-f)^2
 //   models/classification_model.py:21-24   argmax(softmax(F)) == label
-// One CTA per chain walks the rows in a fixed order -> deterministic sums.
+// Small batches: one CTA per chain.  Large batches: up to 64 CTAs per chain write per-CTA partial sums that a
+// second tiny kernel adds in a fixed order -> deterministic either way.
 #include "kernels.cuh"
 
 constexpr int kLikThreads = 1024;
@@ -12,14 +13,15 @@ constexpr int kMaxClasses = 64;
 
 __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
     __shared__ float red[32];
-    const int chain = blockIdx.x;
+    const int chain = blockIdx.y;
     const float* Y = a.Y + chain * a.y_cs;
+    const int64_t row_begin = (int64_t)blockIdx.x * kLikThreads + threadIdx.x, row_step = (int64_t)gridDim.x * kLikThreads;
     float ll_acc = 0.f, g_acc = 0.f;
 
     if (a.likelihood == DGPRF_LIK_GAUSSIAN) {
         const float llv = __ldg(a.lik_log_var + chain * a.h_cs);
         const float inv_var = expf(-llv);
-        for (int64_t row = threadIdx.x; row < a.B; row += kLikThreads) {
+        for (int64_t row = row_begin; row < a.B; row += row_step) {
             float ll = 0.f, se = 0.f;
             for (int j = 0; j < a.D; ++j) {
                 const float f = slab_load(a.F, chain, row, j);
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
             ll_acc += ll;
         }
     } else {
-        for (int64_t row = threadIdx.x; row < a.B; row += kLikThreads) {
+        for (int64_t row = row_begin; row < a.B; row += row_step) {
             float f[kMaxClasses];
             float mx = -INFINITY;
             int arg = 0;
@@ -62,17 +64,46 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
         }
     }
     const float tot = block_sum(ll_acc, red);
-    if (threadIdx.x == 0 && a.ll_sum) a.ll_sum[chain] = tot;
+    const bool multi = gridDim.x > 1;
+    if (threadIdx.x == 0) {
+        if (multi) a.part[((int64_t)chain * gridDim.x + blockIdx.x) * 2] = tot;
+        else if (a.ll_sum) a.ll_sum[chain] = tot;
+    }
     if (a.g_lik_log_var != nullptr) {      // uniform branch
         const float g = block_sum(g_acc, red);
-        if (threadIdx.x == 0) a.g_lik_log_var[chain * a.g_cs] = g * a.inv_B;
+        if (threadIdx.x == 0) {
+            if (multi) a.part[((int64_t)chain * gridDim.x + blockIdx.x) * 2 + 1] = g;
+            else a.g_lik_log_var[chain * a.g_cs] = g * a.inv_B;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) k3_loglik_final(const LikArgs a, int nblk) {
+    const int chain = blockIdx.x;
+    if (threadIdx.x == 0) {
+        float t = 0.f, g = 0.f;
+        for (int i = 0; i < nblk; ++i) {
+            t += a.part[((int64_t)chain * nblk + i) * 2];
+            g += a.part[((int64_t)chain * nblk + i) * 2 + 1];
+        }
+        if (a.ll_sum) a.ll_sum[chain] = t;
+        if (a.g_lik_log_var) a.g_lik_log_var[chain * a.g_cs] = g * a.inv_B;
     }
 }
 
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st) {
     DGPRF_REQUIRE(a.likelihood == DGPRF_LIK_GAUSSIAN || a.D <= kMaxClasses,
                   "softmax with %d classes > %d unsupported", a.D, kMaxClasses);
-    { ProfScope _ps("k3_loglik", st); k3_loglik<<<n_chains, kLikThreads, 0, st>>>(a); }
+    int nblk = 1;
+    if (a.part != nullptr && a.B > 4 * kLikThreads) {
+        nblk = ceil_div(a.B, 2 * kLikThreads);
+        if (nblk > 64) nblk = 64;
+    }
+    { ProfScope _ps("k3_loglik", st); k3_loglik<<<dim3(nblk, n_chains), kLikThreads, 0, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
+    if (nblk > 1 && (a.ll_sum || a.g_lik_log_var)) {
+        k3_loglik_final<<<n_chains, 64, 0, st>>>(a, nblk);
+        DGPRF_CHECK_CUDA(cudaGetLastError());
+    }
     return DGPRF_OK;
 }

@@ -22,10 +22,14 @@ __global__ void __launch_bounds__(256) k5_sgmcmc_update(const UpdArgs a, const _
     const int sub = LPV == 1 ? 0 : (threadIdx.x & (LPV - 1));
     const int64_t nv = ((n4 + 31) / 32) * 32;          // whole warps stay together for the shuffles
     for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPV; v < nv; v += (int64_t)gridDim.x * blockDim.x / LPV) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), th = g, m = g;
+        if (sub == 0 && v < n4) {
+            th = *reinterpret_cast<const float4*>(a.theta + chain * a.cs + (v << 2));
+            m = *reinterpret_cast<const float4*>(a.mom + chain * a.cs + (v << 2));
+        }
         if (v < n4) g = slab_sum_lane<LPV>(grad, a.part_stride, a.n_part, sub, v << 2);
         g = shuffle_sum_lpv<LPV>(g);
-        if (sub == 0 && v < n4) sgmcmc_update_vec(a, tab, chain, v, g);
+        if (sub == 0 && v < n4) sgmcmc_update_vec(a, tab, chain, v, g, th, m);
     }
 }
 

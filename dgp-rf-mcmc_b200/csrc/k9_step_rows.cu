@@ -435,10 +435,14 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         const int sub = tid & 7;
         for (int64_t vb = v0; vb < v1; vb += kST / 8) {                 // 8 lanes per vector, 64 vectors per pass
             const int64_t v = vb + (tid >> 3);
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f), th = g, m = g;
+            if (sub == 0 && v < v1) {
+                th = *reinterpret_cast<const float4*>(a.upd.theta + chain * a.upd.cs + (v << 2));
+                m = *reinterpret_cast<const float4*>(a.upd.mom + chain * a.upd.cs + (v << 2));
+            }
             if (v < v1) g = slab_sum_lane<8>(grad, a.upd.part_stride, a.upd.n_part, sub, v << 2);
             g = shuffle_sum_lpv<8>(g);
-            if (sub == 0 && v < v1) sgmcmc_update_vec(a.upd, tab, chain, v, g);
+            if (sub == 0 && v < v1) sgmcmc_update_vec(a.upd, tab, chain, v, g, th, m);
         }
         if (a.u_out != nullptr && grp == 0 && tid < 32) {               // minibatch log-likelihood, fixed order
             float s = 0.f;

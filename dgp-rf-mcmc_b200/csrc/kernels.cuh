@@ -12,6 +12,7 @@ struct LikArgs {
     float* dF; int64_t df_cs;           // [C][B][D] nullable (needs inv_B)
     float* g_lik_log_var; int64_t g_cs; // nullable: dU/d lik_log_var (data term)
     float* probs;                       // softmax only, nullable [C][B][D]
+    float* part;                        // [C][64][2] per-CTA partial sums for large batches (nullable: one CTA)
     float inv_B;
 };
 

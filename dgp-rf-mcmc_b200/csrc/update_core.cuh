@@ -16,6 +16,7 @@ struct SegTable {
 // the lanes with shuffle_sum_lpv).  All loads of a batch are in flight before the fixed-order adds.
 template <int LPV>
 __device__ __forceinline__ float4 slab_sum_lane(const float* __restrict__ grad, int64_t part_stride, int n_part, int sub, int64_t i) {
+    if (LPV == 1 && n_part == 1) return __ldcg(reinterpret_cast<const float4*>(grad + i));     // dense gradient
     float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p0 = sub; p0 < n_part; p0 += 8 * LPV) {
         float4 gp[8];
@@ -38,8 +39,10 @@ __device__ __forceinline__ float4 shuffle_sum_lpv(float4 g) {
     return g;
 }
 
-// Update the four parameters at flat offset i = 4*i4 of `chain` given their summed data gradient g.
-__device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTable& tab, int chain, int64_t i4, float4 g) {
+// Update the four parameters at flat offset i = 4*i4 of `chain` given their summed data gradient g and the
+// current values th / m (loaded by the caller together with the gradient so all three are in flight at once).
+__device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTable& tab, int chain, int64_t i4, float4 g,
+                                                  float4 th, float4 m) {
     const int64_t i = i4 << 2;
     float* theta = a.theta + chain * a.cs;
     float* mom = a.mom + chain * a.cs;
@@ -53,8 +56,6 @@ __device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTab
     const float sqrt_mass = tab.sqrt_mass[lo], inv_mass = tab.inv_mass[lo];
     const bool prior = tab.flags[lo] & 1;
 
-    float4 th = *reinterpret_cast<const float4*>(theta + i);
-    float4 m = *reinterpret_cast<const float4*>(mom + i);
     if (prior) {
         g.x = fmaf(th.x, a.inv_N, g.x); g.y = fmaf(th.y, a.inv_N, g.y);
         g.z = fmaf(th.z, a.inv_N, g.z); g.w = fmaf(th.w, a.inv_N, g.w);

@@ -49,6 +49,10 @@ for prec in ("fp32", "tf32"):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 5
     out[f"{prec}_fwd_bwd"] = {"ms": ms, "tflops": (fwd_flops + bwd_flops) / ms / 1e9}
+    # per-kernel times of one gradient pass (library event hook)
+    _ffi.profile_start()
+    e.gradients(X, Y, 1e5, hyper=False, prior_w=True, prior_h=False)
+    out[f"{prec}_kernels_ms"] = {nm: round(ms_, 4) for nm, ms_ in _ffi.profile_stop()}
     del e
     torch.cuda.empty_cache()
 print(json.dumps(out, indent=1))
