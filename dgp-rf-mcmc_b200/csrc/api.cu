@@ -479,7 +479,7 @@ extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x
 }
 
 extern "C" int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host, const float* Y_host, int y_cols, int B,
-                                      float* X_dev, float* Y_dev, int full_bayesian,
+                                      float* X_dev, float* Y_dev, int zero_copy, int full_bayesian,
                                       float* theta_w, float* mom_w, int64_t w_len,
                                       const dgprf_segment* segs_w, int n_seg_w,
                                       float* theta_h, float* mom_h, int64_t h_len,
@@ -490,6 +490,11 @@ extern "C" int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host,
     DGPRF_REQUIRE(m && X_host && Y_host && X_dev && Y_dev && B >= 1 && y_cols >= 1, "step_host: bad arguments");
     DGPRF_REQUIRE(u_host == nullptr || u_dev != nullptr, "step_host: u_host needs the u_dev staging word");
     cudaStream_t st = (cudaStream_t)stream;
+    if (zero_copy)       // pinned host buffers are device-visible: no staging copies, one launch
+        return dgprf_sgmcmc_step(m, X_host, 0, Y_host, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,
+                                 theta_h, mom_h, h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature,
+                                 resample_moments, seed, step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes,
+                                 u_host, stream);
     DGPRF_CHECK_CUDA(cudaMemcpyAsync(X_dev, X_host, sizeof(float) * (size_t)B * m->d_in, cudaMemcpyHostToDevice, st));
     DGPRF_CHECK_CUDA(cudaMemcpyAsync(Y_dev, Y_host, sizeof(float) * (size_t)B * y_cols, cudaMemcpyHostToDevice, st));
     const int rc = dgprf_sgmcmc_step(m, X_dev, 0, Y_dev, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,

@@ -250,9 +250,9 @@ class DGP_RF:
             self._sampler_ready[bool(full_bayesian)] = True
         e = self._engine
         self._step += 1
-        if (eps is None and resample is None and torch.is_tensor(X_batch) and torch.is_tensor(Y_batch)
-                and X_batch.device.type == "cpu" and X_batch.dtype == torch.float32 and Y_batch.dtype == torch.float32
-                and X_batch.ndim == 2 and Y_batch.ndim == 2 and X_batch.is_contiguous() and Y_batch.is_contiguous()
+        if (eps is None and resample is None and type(X_batch) is torch.Tensor and type(Y_batch) is torch.Tensor
+                and not X_batch.is_cuda and X_batch.dtype is torch.float32 and Y_batch.dtype is torch.float32
+                and X_batch.dim() == 2 and Y_batch.dim() == 2 and X_batch.is_contiguous() and Y_batch.is_contiguous()
                 and e.device.type == "cuda"):
             # host minibatch: H2D copies + step enqueued by one C call (dgprf_sgmcmc_step_host)
             e.step_host(X_batch, Y_batch, float(data_size), float(lr), float(momentum_decay), float(temperature),
