@@ -225,9 +225,10 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
-        const int rc = (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a))
-                           ? dgprf_launch_fwd_tc(a, m->n_chains, st)
-                           : dgprf_launch_fwd_simt(a, m->n_chains, st);
+        int rc;
+        if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);   // pipelined
+        else if (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a)) rc = dgprf_launch_fwd_tc(a, m->n_chains, st);
+        else rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
         if (rc) return rc;
     }
     if (F_out) {

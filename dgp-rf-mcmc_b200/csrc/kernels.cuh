@@ -40,6 +40,8 @@ struct HypArgs {
 
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_fwd_tc_supported(const FwdArgs& a);
+bool dgprf_fwd_tc2_supported(const FwdArgs& a);
+int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_bwd_tc_supported(const BwdArgs& a);

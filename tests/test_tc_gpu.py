@@ -29,6 +29,9 @@ CASES = {
     "two_tiles_per_cta_mean": (RegressionDGP, 5, 2, 2, [1024, 68], [40, 2], ["RBF", "ARC"], True, True, 130),
     "wide_input_kgroups": (ClassificationDGP, 200, 4, 2, 128, [33, 4], ["ARC", "RBF"], True, False, 257),
     "tiny": (RegressionDGP, 1, 1, 2, 100, [1, 1], None, False, False, 20),
+    # grids large enough for the pipelined (warp-specialised, A-in-TMEM) forward kernel k1_fwd_tc2
+    "pipelined_rbf_mean": (RegressionDGP, 9, 1, 3, 512, [9, 9, 1], None, True, True, 2048),
+    "pipelined_arc_wide": (ClassificationDGP, 100, 10, 2, [512, 320], [28, 10], ["ARC", "RBF"], True, False, 2100),
 }
 
 
