@@ -71,6 +71,8 @@ struct LayerWs {
     int tc_cols;   // 0: SIMT forward; 32 | 64: tensor-core forward with that column-tile width
     int64_t n_phi, n_fpart, n_dpart, n_tpart, n_rpart;       // floats per chain
     size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
+    int tc2;                                                 // pipelined TC forward: prepped operand buffers below
+    int64_t n_zt, n_wt; size_t zt, wt;
 };
 struct WsLayout {
     LayerWs L[DGPRF_MAX_LAYERS];
@@ -127,6 +129,8 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
             s.tc_cols = dgprf_tc_tile_cols(B, y.M, m->n_chains);
             const int t = ceil_div(y.M, s.tc_cols);
             s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : s.CS;
+            const int c2 = dgprf_fwd_tc2_col_splits(s.tc_cols, B, layer_d(y), y.M, y.g, m->n_chains);
+            if (c2 > 0) { s.tc2 = 1; s.CSf = c2; }
         }
         s.n_fpart = (int64_t)s.CSf * B * y.g;
         s.fpart = take(s.n_fpart);
@@ -138,6 +142,12 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         if (mode == DGPRF_MODE_HYPER) {
             s.n_tpart = (int64_t)s.CS * B * layer_d(y); s.tpart = take(s.n_tpart);
             s.n_rpart = (int64_t)s.CS * B;              s.rpart = take(s.n_rpart);
+        }
+        if (s.tc2) {
+            s.n_zt = dgprf_fwd_tc2_zt_floats(y.M);          // one copy per chain (only the first is used when z is shared)
+            s.zt = take(s.n_zt);
+            s.n_wt = dgprf_fwd_tc2_wt_floats(layer_F(y), y.g);
+            s.wt = take(s.n_wt);
         }
         const int64_t wend = y.off_W + (int64_t)layer_F(y) * y.g;
         if (wend > w->w_len) w->w_len = wend;
@@ -225,6 +235,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
+        if (w.L[l].tc2) { a.zt = wsf(ws, w.L[l].zt); a.wt = wsf(ws, w.L[l].wt); }
         int rc;
         if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);   // pipelined
         else if (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a)) rc = dgprf_launch_fwd_tc(a, m->n_chains, st);

@@ -82,6 +82,7 @@ struct FwdArgs {
     const float* W;  int64_t w_cs;       // [F, g]
     float* Phi;      int64_t phi_cs;     // [B, F] nullable
     float* Fpart;    int64_t fpart_cs;   // [CS][B][g]
+    float* zt; int64_t zt_cs; float* wt; // pipelined TC forward: prepped z^T hi/lo [2][M][128] and W^T [NG][F] (workspace)
 };
 
 struct BwdArgs {

@@ -6,17 +6,20 @@
 //     so shared memory only holds the streamed operands;
 //   * roles:  warps 0-7  epilogue   tcgen05.ld P -> sincos/relu -> Phi tile (smem, UMMA/TMA swizzle)
 //             warp  8    MMA        one thread issues GEMM #1 (3xTF32) of tile t+1 and GEMM #2 of tile t
-//             warps 9-11 stagers    z tile (hi/lo) and W tile of the next column tile -> smem
-//             warp  12   store      TMA store of the Phi tile (saved features)
-//     connected by mbarriers; P (D1) is double-buffered in TMEM so GEMM #1 of tile t+1 and the staging of its
-//     operands run under the epilogue of tile t (the MUFU/issue-bound part).
+//             warp  9    producer   one thread issues the TMA loads of the next z tile (tf32 hi/lo) and W tile
+//             warp  10   store      TMA store of the Phi tile (saved features)
+//     connected by mbarriers; P (D1) is double-buffered in TMEM and the z tile is a 2-stage ring (when it
+//     fits), so GEMM #1 of tile t+1 and the loads of tile t+2 run under the epilogue of tile t.
+//   * the streamed operands are pre-laid for TMA by a small prep kernel per launch: z^T split into tf32
+//     hi/lo, K-major, zero-padded to 128 K columns ([2][M][128]) and W^T rounded to tf32 ([NG][F]).
 #include <stdlib.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
 constexpr int V2_BM = 128, V2_BN = 64;
-constexpr int V2_EPI_WARPS = 8, V2_STAGE_WARPS = 3;
-constexpr int V2_THREADS = (V2_EPI_WARPS + 1 + V2_STAGE_WARPS + 1) * 32;      // 416
+constexpr int V2_EPI_WARPS = 8;
+constexpr int V2_THREADS = (V2_EPI_WARPS + 3) * 32;                           // 352
+constexpr int V2_HDR = 1024;                      // bias row + mbarriers + TMEM slot
 constexpr int V2_BLK = V2_BM * 128;               // [128 x 32 tf32] block
 constexpr int V2_BBLK = V2_BN * 128;              // [64 x 32 tf32] block
 constexpr int V2_KB = 4;                          // K blocks of GEMM #1 (input width <= 128)
@@ -45,30 +48,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int NG>
 __global__ void __launch_bounds__(V2_THREADS, 1)
-k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin) {
+k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
+           const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sB1 = sm;                                   // [hi blocks 0..KB) | lo blocks 0..KB)] of [64 x 32]
-    uint8_t* sPhi = sB1 + 2 * V2_KB * V2_BBLK;           // 4 blocks [128 x 32]: cos 0,1 | sin 2,3
+    float* bias_s = reinterpret_cast<float*>(sm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_BM * sizeof(float));
+    uint8_t* sPhi = sm + V2_HDR;                         // 4 blocks [128 x 32]: cos 0,1 | sin 2,3
     uint8_t* sW = sPhi + 4 * V2_BLK;                     // 2 stages x 4 blocks [NG x 32]
-    float* bias_s = reinterpret_cast<float*>(sW + 2 * 4 * NG * 128);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + V2_BM);
-    uint64_t* b1_full = bars + 0;     // stagers (3 warps)        -> MMA
-    uint64_t* b1_empty = bars + 1;    // MMA commit               -> stagers
-    uint64_t* d1_full = bars + 2;     // [2] MMA commit           -> epilogue
-    uint64_t* d1_empty = bars + 4;    // [2] epilogue (8 warps)   -> MMA
-    uint64_t* phi_full = bars + 6;    // epilogue (8 warps)       -> MMA, store
-    uint64_t* phi_empty = bars + 7;   // MMA commit + store warp  -> epilogue      (count 2)
-    uint64_t* w_full = bars + 8;      // [2] stagers              -> MMA
-    uint64_t* w_empty = bars + 10;    // [2] MMA commit           -> stagers
-    uint64_t* d2_full = bars + 12;    // MMA commit               -> final epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint8_t* sB1 = sW + 2 * 4 * NG * 128;                // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
+    uint64_t* b1_full = bars + 0;     // [2] TMA complete_tx      -> MMA
+    uint64_t* b1_empty = bars + 2;    // [2] MMA commit           -> producer
+    uint64_t* d1_full = bars + 4;     // [2] MMA commit           -> epilogue
+    uint64_t* d1_empty = bars + 6;    // [2] epilogue (8 warps)   -> MMA
+    uint64_t* phi_full = bars + 8;    // epilogue (8 warps)       -> MMA, store
+    uint64_t* phi_empty = bars + 9;   // MMA commit + store warp  -> epilogue      (count 2)
+    uint64_t* w_full = bars + 10;     // [2] TMA complete_tx      -> MMA
+    uint64_t* w_empty = bars + 12;    // [2] MMA commit           -> producer
+    uint64_t* d2_full = bars + 14;    // MMA commit               -> final epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chain = blockIdx.z, cs = blockIdx.y, row0 = blockIdx.x * V2_BM;
-    const float* z = a.z + chain * a.z_cs;
     const float* X = a.X + chain * a.x_cs;
-    const float* W = a.W + chain * a.w_cs;
     const float* ls = a.log_inv_ls + chain * a.h_cs;
     const float* mean = a.has_mean ? a.mean + chain * a.h_cs : nullptr;
     const bool rbf = a.kind == DGPRF_KIND_RBF;
@@ -77,15 +79,16 @@ k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const int n_my = cs < n_ct ? (n_ct - cs + a.CS - 1) / a.CS : 0;        // column tiles of this CTA
     const int n_kb = (a.d + 31) / 32;
     const int nb2 = rbf ? 4 : 2;
+    const uint32_t b1_stage = 2u * n_kb * V2_BBLK;
 
     if (warp == V2_EPI_WARPS) tc::tmem_alloc(tmem_slot, V2_TMEM_COLS);
     if (tid == 0) {
-        tc::mbar_init(b1_full, V2_STAGE_WARPS);
-        tc::mbar_init(b1_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(b1_full + i, 1);
+            tc::mbar_init(b1_empty + i, 1);
             tc::mbar_init(d1_full + i, 1);
             tc::mbar_init(d1_empty + i, V2_EPI_WARPS);
-            tc::mbar_init(w_full + i, V2_STAGE_WARPS);
+            tc::mbar_init(w_full + i, 1);
             tc::mbar_init(w_empty + i, 1);
         }
         tc::mbar_init(phi_full, V2_EPI_WARPS);
@@ -99,36 +102,53 @@ k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_ahi = tmem_base, tm_alo = tmem_base + 128, tm_d1 = tmem_base + 256, tm_d2 = tmem_base + 384;
 
-    // ---- A operand -> TMEM (epilogue warps: thread = row, warp half = 64 K columns) ----
-    if (warp < V2_EPI_WARPS) {
-        const int lq = warp & 3, kh = warp >> 2;
-        const int r = 32 * lq + lane;
-        const int64_t row = row0 + r;
-        float bsum = 0.f;
+    // ---- A operand -> TMEM.  The 128-row input tile is first read coalesced into shared memory (it borrows the
+    //      Phi / W regions, idle until the pipeline starts), then each epilogue thread owns one row x 64 K columns.
+    {
+        float* sIn = reinterpret_cast<float*>(sPhi);          // [128][129]
+        float* sSq = reinterpret_cast<float*>(sB1);           // [128] exp(log_inv_ls) | [128] mean
+        float* sMean = sSq + 128;
+        if (tid < 128) {
+            sSq[tid] = tid < a.d ? expf(__ldg(ls + tid)) : 0.f;
+            sMean[tid] = (mean != nullptr && tid < a.d) ? __ldg(mean + tid) : 0.f;
+        }
+        for (int r = warp; r < V2_BM; r += V2_THREADS / 32) {
+            const int64_t row = row0 + r;
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-            float hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int q = 64 * kh + 16 * c16 + i;
+            for (int q = lane; q < 128; q += 32) {
                 float v = 0.f;
                 if (row < a.B && q < a.d)
                     v = q < a.d_prev ? slab_load(a.Fprev, chain, row, q) : __ldg(X + row * a.ldx + (q - a.d_prev));
-                const float sq = q < a.d ? expf(__ldg(ls + q)) : 0.f;
-                if (mean && q < a.d) bsum = fmaf(v, __ldg(mean + q), bsum);
-                const float x = v * sq;
-                hi[i] = tc::to_tf32(x);
-                lo[i] = tc::to_tf32(x - hi[i]);
+                sIn[r * 129 + q] = v;
             }
-            const uint32_t col = 64 * kh + 16 * c16;
-            tc::tmem_st16(tm_ahi + ((uint32_t)(32 * lq) << 16) + col, hi);
-            tc::tmem_st16(tm_alo + ((uint32_t)(32 * lq) << 16) + col, lo);
         }
-        tc::tmem_st_wait();
-        if (a.has_mean) {                         // bias_r = sum_q in[r][q] mean[q]: the two K halves of a row
-            if (kh == 0) bias_s[r] = bsum;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (kh == 1) bias_s[r] += bsum;
+        __syncthreads();
+        if (warp < V2_EPI_WARPS) {
+            const int lq = warp & 3, kh = warp >> 2;
+            const int r = 32 * lq + lane;
+            float bsum = 0.f;
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int q = 64 * kh + 16 * c16 + i;
+                    const float v = sIn[r * 129 + q];
+                    bsum = fmaf(v, sMean[q], bsum);
+                    const float x = v * sSq[q];
+                    hi[i] = tc::to_tf32(x);
+                    lo[i] = tc::to_tf32(x - hi[i]);
+                }
+                const uint32_t col = 64 * kh + 16 * c16;
+                tc::tmem_st16(tm_ahi + ((uint32_t)(32 * lq) << 16) + col, hi);
+                tc::tmem_st16(tm_alo + ((uint32_t)(32 * lq) << 16) + col, lo);
+            }
+            tc::tmem_st_wait();
+            if (a.has_mean) {                     // bias_r = sum_q in[r][q] mean[q]: the two K halves of a row
+                if (kh == 0) bias_s[r] = bsum;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (kh == 1) bias_s[r] += bsum;
+            }
         }
     }
     tc::tc_fence_before();
@@ -206,22 +226,24 @@ k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             for (int t = 0; t <= n_my; ++t) {
                 if (t < n_my) {
                     const int buf = t & 1;
+                    const int s1 = t % NS1;
+                    const uint32_t b1 = tc::smem_u32(sB1) + s1 * b1_stage;
                     tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
-                    tc::mbar_wait(b1_full, t & 1);
+                    tc::mbar_wait(b1_full + s1, (t / NS1) & 1);
                     tc::tc_fence_after();
                     for (int kb = 0; kb < n_kb; ++kb) {
                         const int kleft = a.d - 32 * kb;
                         const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
                         for (int k4 = 0; k4 < ksteps; ++k4) {
                             const uint32_t acol = 32 * kb + 8 * k4;
-                            const uint64_t dbh = tc::make_desc_sw128(tc::smem_u32(sB1 + kb * V2_BBLK) + k4 * 32);
-                            const uint64_t dbl = tc::make_desc_sw128(tc::smem_u32(sB1 + (V2_KB + kb) * V2_BBLK) + k4 * 32);
+                            const uint64_t dbh = tc::make_desc_sw128(b1 + kb * V2_BBLK + k4 * 32);
+                            const uint64_t dbl = tc::make_desc_sw128(b1 + (n_kb + kb) * V2_BBLK + k4 * 32);
                             tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_alo + acol, dbh, IDESC1, (kb | k4) != 0);
                             tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_ahi + acol, dbl, IDESC1, 1u);
                             tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_ahi + acol, dbh, IDESC1, 1u);
                         }
                     }
-                    tc::umma_commit(b1_empty);             // z tile consumed
+                    tc::umma_commit(b1_empty + s1);        // z tile consumed
                     tc::umma_commit(d1_full + buf);        // P ready
                 }
                 if (t > 0) {
@@ -242,79 +264,30 @@ k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 }
             }
         }
-    } else if (warp < V2_EPI_WARPS + 1 + V2_STAGE_WARPS) {
-        // ===================================== STAGERS =====================================
-        const int st = tid - (V2_EPI_WARPS + 1) * 32;                // 0..95
-        constexpr int NST = V2_STAGE_WARPS * 32;
-        for (int t = 0; t < n_my; ++t) {
-            const int c0 = (cs + t * a.CS) * V2_BN;
-            // ---- z tile (B of GEMM #1): rows = feature columns, 16-byte chunks along K, tf32 hi / lo ----
-            tc::mbar_wait(b1_empty, (t & 1) ^ 1);
-            {
-                constexpr int ZB = 6;                                  // items (4 loads each) in flight per thread
-                const int n_items = n_kb * V2_BN * 8;
-                for (int e0 = st; e0 < n_items; e0 += NST * ZB) {
-                    float zx[ZB][4];
-#pragma unroll
-                    for (int u = 0; u < ZB; ++u) {
-                        const int e = e0 + u * NST;
-                        const int n = e % V2_BN, ch = (e / V2_BN) & 7, kb = e / (V2_BN * 8);
-                        const int col = c0 + n;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int q = kb * 32 + ch * 4 + i;
-                            zx[u][i] = (e < n_items && q < a.d && col < a.M) ? __ldg(z + (int64_t)q * a.M + col) : 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < ZB; ++u) {
-                        const int e = e0 + u * NST;
-                        if (e < n_items) {
-                            const int n = e % V2_BN, ch = (e / V2_BN) & 7, kb = e / (V2_BN * 8);
-                            float4 o, ol;
-                            o.x = tc::to_tf32(zx[u][0]); o.y = tc::to_tf32(zx[u][1]); o.z = tc::to_tf32(zx[u][2]); o.w = tc::to_tf32(zx[u][3]);
-                            ol.x = tc::to_tf32(zx[u][0] - o.x); ol.y = tc::to_tf32(zx[u][1] - o.y);
-                            ol.z = tc::to_tf32(zx[u][2] - o.z); ol.w = tc::to_tf32(zx[u][3] - o.w);
-                            *reinterpret_cast<float4*>(sB1 + kb * V2_BBLK + tc::sw128_chunk(n, ch)) = o;
-                            *reinterpret_cast<float4*>(sB1 + (V2_KB + kb) * V2_BBLK + tc::sw128_chunk(n, ch)) = ol;
-                        }
-                    }
+    } else if (warp == V2_EPI_WARPS + 1) {
+        // ===================================== TMA PRODUCER =====================================
+        if (lane == 0) {
+            const int zc = a.zt_cs != 0 ? chain : 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int c0 = (cs + t * a.CS) * V2_BN;
+                // ---- z tile (B of GEMM #1): rows = feature columns, K-major, tf32 hi blocks then lo blocks ----
+                const int s1 = t % NS1;
+                tc::mbar_wait(b1_empty + s1, ((t / NS1) & 1) ^ 1);
+                tc::mbar_expect_tx(b1_full + s1, b1_stage);
+                const uint32_t b1 = tc::smem_u32(sB1) + s1 * b1_stage;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    tc::tma_load_3d(&map_zt, b1 + kb * V2_BBLK, b1_full + s1, 32 * kb, c0, 2 * zc);
+                    tc::tma_load_3d(&map_zt, b1 + (n_kb + kb) * V2_BBLK, b1_full + s1, 32 * kb, c0, 2 * zc + 1);
                 }
-            }
-            tc::fence_async_smem();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(b1_full);
-            // ---- W tile (B of GEMM #2) into ring stage t & 1 ----
-            if (a.do_gemm2) {
-                const int ws = t & 1;
-                tc::mbar_wait(w_empty + ws, ((t >> 1) & 1) ^ 1);
-                uint8_t* dstW = sW + ws * 4 * (NG * 128);
-                {
-                    constexpr int WB = 16;                             // loads in flight per thread
-                    const int n_el = nb2 * 32 * NG;
-                    for (int e0 = st; e0 < n_el; e0 += NST * WB) {
-                        float wv[WB];
-#pragma unroll
-                        for (int u = 0; u < WB; ++u) {
-                            const int e = e0 + u * NST;
-                            const int j = e % NG, kf = e / NG;
-                            const int col = c0 + (kf & 63);
-                            const int64_t frow = (kf >= 64 ? a.M : 0) + col;
-                            wv[u] = (e < n_el && j < a.g && col < a.M) ? __ldg(W + frow * a.g + j) : 0.f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < WB; ++u) {
-                            const int e = e0 + u * NST;
-                            if (e < n_el) {
-                                const int j = e % NG, kf = e / NG;
-                                *reinterpret_cast<float*>(dstW + (kf >> 5) * (NG * 128) + tc::sw128_off(j, kf & 31)) = tc::to_tf32(wv[u]);
-                            }
-                        }
-                    }
+                // ---- W^T tile (B of GEMM #2) into ring stage t & 1 ----
+                if (a.do_gemm2) {
+                    const int ws = t & 1;
+                    tc::mbar_wait(w_empty + ws, ((t >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(w_full + ws, (uint32_t)nb2 * NG * 128);
+                    for (int b = 0; b < nb2; ++b)
+                        tc::tma_load_3d(&map_wt, tc::smem_u32(sW + (ws * 4 + b) * (NG * 128)), w_full + ws,
+                                        (b >= 2 ? a.M : 0) + c0 + 32 * (b & 1), 0, chain);
                 }
-                tc::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(w_full + ws);
             }
         }
     } else {
@@ -342,19 +315,68 @@ k1_fwd_tc2(const FwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     if (warp == V2_EPI_WARPS) tc::tmem_dealloc(tmem_base, V2_TMEM_COLS);
 }
 
-static size_t tc2_smem_bytes(int NG) {
-    return 1024 + 2 * (size_t)V2_KB * V2_BBLK + 4 * (size_t)V2_BLK + 2 * 4 * (size_t)NG * 128 + V2_BM * sizeof(float) + 16 * 8 + 16;
+// ---- operand prep: z [d, M] -> zt [2][M][128] (tf32 hi | lo, K-major, zero padded); W [F, g] -> wt [NG][F] (tf32) ----
+__global__ void __launch_bounds__(256)
+k_prep_tc2(const float* __restrict__ z, int64_t z_cs, int d, int M, float* __restrict__ zt, int n_zt_tiles,
+           const float* __restrict__ W, int64_t w_cs, int F, int g, int NG, float* __restrict__ wt, int64_t wt_cs) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int chain = blockIdx.y;
+    int b = blockIdx.x;
+    if (b < n_zt_tiles) {
+        if (z_cs == 0 && chain > 0) return;                           // shared spectral draws: one copy
+        const int m0 = (b >> 2) * 32, k0 = (b & 3) * 32;
+        const float* zz = z + chain * z_cs;
+        for (int i = ty; i < 32; i += 8)
+            tile[i][tx] = (k0 + i < d && m0 + tx < M) ? __ldg(zz + (int64_t)(k0 + i) * M + m0 + tx) : 0.f;
+        __syncthreads();
+        float* hi = zt + (int64_t)chain * 2 * M * 128;
+        float* lo = hi + (int64_t)M * 128;
+        for (int i = ty; i < 32; i += 8)
+            if (m0 + i < M) {
+                const float v = tile[tx][i];
+                const float h = tc::to_tf32(v);
+                hi[(int64_t)(m0 + i) * 128 + k0 + tx] = h;
+                lo[(int64_t)(m0 + i) * 128 + k0 + tx] = tc::to_tf32(v - h);
+            }
+        return;
+    }
+    b -= n_zt_tiles;
+    const int nj = (NG + 31) / 32;
+    const int f0 = (b / nj) * 32, j0 = (b % nj) * 32;
+    const float* WW = W + chain * w_cs;
+    for (int i = ty; i < 32; i += 8)
+        tile[i][tx] = (f0 + i < F && j0 + tx < g) ? __ldg(WW + (int64_t)(f0 + i) * g + j0 + tx) : 0.f;
+    __syncthreads();
+    float* o = wt + chain * wt_cs;
+    for (int i = ty; i < 32; i += 8)
+        if (j0 + i < NG && f0 + tx < F) o[(int64_t)(j0 + i) * F + f0 + tx] = tc::to_tf32(tile[tx][i]);
+}
+
+static size_t tc2_smem_bytes(int NG, int n_kb, int ns1) {
+    return 1024 + V2_HDR + 4 * (size_t)V2_BLK + 2 * 4 * (size_t)NG * 128 + (size_t)ns1 * 2 * n_kb * V2_BBLK;
 }
 
 template <int NG>
 static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
-    const size_t smem = tc2_smem_bytes(NG);
+    const int n_kb = (a.d + 31) / 32;
+    const int ns1 = tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1;
+    const size_t smem = tc2_smem_bytes(NG, n_kb, ns1);
     static bool configured = false;
     if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
-    CUtensorMap mc, ms;
+    DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
+    {
+        const int n_zt_tiles = ceil_div(a.M, 32) * 4;
+        const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
+        ProfScope _ps("k_prep_tc2", st);
+        k_prep_tc2<<<dim3(n_zt_tiles + n_wt_tiles, n_chains), 256, 0, st>>>(a.z, a.z_cs, a.d, a.M, a.zt, n_zt_tiles,
+                                                                          a.W, a.w_cs, a.F, a.g, NG, a.wt, (int64_t)NG * a.F);
+        DGPRF_CHECK_CUDA(cudaGetLastError());
+    }
+    CUtensorMap mc, ms, mz, mw;
     memset(&mc, 0, sizeof(mc));
     memset(&ms, 0, sizeof(ms));
     if (a.Phi != nullptr) {
@@ -365,20 +387,41 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
             if (rc) return rc;
         }
     }
+    int rc = dgprf_make_tmap_3d(&mz, a.zt, 128, a.M, 2 * (a.z_cs != 0 ? n_chains : 1), 128, (uint64_t)a.M * 128, V2_BN);
+    if (rc) return rc;
+    rc = dgprf_make_tmap_3d(&mw, a.wt, a.F, NG, n_chains, a.F, (uint64_t)NG * a.F, NG);
+    if (rc) return rc;
+    FwdArgs b = a;
+    b.zt_cs = a.z_cs != 0 ? 1 : 0;
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG><<<grid, V2_THREADS, smem, st>>>(a, mc, ms); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG><<<grid, V2_THREADS, smem, st>>>(b, ns1, mc, ms, mz, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
 
-// the pipelined kernel takes 64-column tiles and an input width that fits the TMEM-resident A operand
-bool dgprf_fwd_tc2_supported(const FwdArgs& a) {
-    return a.tile_cols == 64 && a.d <= 128 && (a.M % 4 == 0) && a.g <= 64 && (a.Phi == nullptr || (a.phi_cs % 4) == 0) &&
-           getenv("DGPRF_NO_TC2") == nullptr;
+// The pipelined kernel takes 64-column tiles and an input width that fits the TMEM-resident A operand.  Returns the
+// number of column splits (CTAs per row block; each walks M/64/splits column tiles) or 0 when the layered v1
+// kernel should run instead: the per-CTA prologue and pipeline fill only pay off over >= 4 tiles per CTA.
+int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains) {
+    if (tile_cols != 64 || d > 128 || (M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
+    const int n_ct = ceil_div(M, V2_BN);
+    const int64_t rb = (int64_t)ceil_div(B, V2_BM) * n_chains;
+    int cs = (int)((4 * 148 + rb - 1) / rb);                   // >= 4 waves of CTAs when the problem allows
+    if (cs > kMaxCS) cs = kMaxCS;
+    if (cs > n_ct) cs = n_ct;
+    if (cs < 1) cs = 1;
+    while (cs > 1 && n_ct / cs < 4) --cs;
+    return n_ct / cs >= 4 ? cs : 0;
 }
+bool dgprf_fwd_tc2_supported(const FwdArgs& a) {
+    return a.zt != nullptr && a.wt != nullptr && (a.Phi == nullptr || (a.phi_cs % 4) == 0);
+}
+// floats of the prepped operand buffers: zt per spectral-draw copy, wt per chain
+int64_t dgprf_fwd_tc2_zt_floats(int M) { return 2 * (int64_t)M * 128; }
+int64_t dgprf_fwd_tc2_wt_floats(int F, int g) { return (int64_t)(g <= 16 ? 16 : g <= 32 ? 32 : 64) * F; }
 
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
-    const int g = a.do_gemm2 ? a.g : 1;
+    const int g = a.g;
     if (g <= 16) return launch_fwd_tc2<16>(a, n_chains, st);
     if (g <= 32) return launch_fwd_tc2<32>(a, n_chains, st);
     return launch_fwd_tc2<64>(a, n_chains, st);

@@ -89,6 +89,13 @@ def test_tc_saved_features_and_gradients(name):
     Bn = X.shape[0]
     ctas64 = ((Bn + 127) // 128) * min((s0.M + 63) // 64, 8)
     CS = min((s0.M + 31) // 32, 16) if ctas64 < 120 else min((s0.M + 63) // 64, 8)   # dgprf_tc_tile_cols
+    if ctas64 >= 120 and s0.d <= 128:                                                 # dgprf_fwd_tc2_col_splits
+        n_ct, rb = (s0.M + 63) // 64, (Bn + 127) // 128
+        c2 = max(1, min((4 * 148 + rb - 1) // rb, 8, n_ct))
+        while c2 > 1 and n_ct // c2 < 4:
+            c2 -= 1
+        if n_ct // c2 >= 4:
+            CS = c2
     off = ((CS * Bn * s0.g * 4 + 255) // 256) * 256
     Phi0 = ws[off:off + X.shape[0] * s0.F * 4].view(torch.float32).view(X.shape[0], s0.F)
     assert rel_err(Phi0, Phis[0]) < 1e-4
