@@ -41,6 +41,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane of a CONVERGED warp; tells the compiler the guarded region is single-threaded, so the uniform-datapath
+// tcgen05 instructions inside are issued without a per-lane uniformity loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -221,52 +228,64 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
         }
     } else if (warp == V2_EPI_WARPS) {
         // ===================================== MMA ISSUER =====================================
-        if (lane == 0) {
-            // software pipeline: GEMM #1 of tile t is issued before GEMM #2 of tile t-1
-            for (int t = 0; t <= n_my; ++t) {
-                if (t < n_my) {
-                    const int buf = t & 1;
-                    const int s1 = t % NS1;
-                    const uint32_t b1 = tc::smem_u32(sB1) + s1 * b1_stage;
-                    tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
-                    tc::mbar_wait(b1_full + s1, (t / NS1) & 1);
-                    tc::tc_fence_after();
+        // The whole warp walks the loop converged (waits included); one elected lane issues.  Descriptors are
+        // built once: advancing along K or to another block only adds to the 14-bit start-address field.
+        const uint64_t dB1 = tc::make_desc_sw128(tc::smem_u32(sB1));
+        const uint64_t dPhi = tc::make_desc_sw128(tc::smem_u32(sPhi));
+        const uint64_t dW = tc::make_desc_sw128(tc::smem_u32(sW));
+        const uint32_t lo_off = (uint32_t)(n_kb * V2_BBLK) >> 4;
+        // software pipeline: GEMM #1 of tile t is issued before GEMM #2 of tile t-1
+        for (int t = 0; t <= n_my; ++t) {
+            if (t < n_my) {
+                const int buf = t & 1;
+                const int s1 = t % NS1;
+                tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
+                tc::mbar_wait(b1_full + s1, (t / NS1) & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint64_t db = dB1 + ((s1 * b1_stage) >> 4);
+                    const uint32_t dcol = tm_d1 + 64 * buf;
                     for (int kb = 0; kb < n_kb; ++kb) {
                         const int kleft = a.d - 32 * kb;
                         const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
                         for (int k4 = 0; k4 < ksteps; ++k4) {
                             const uint32_t acol = 32 * kb + 8 * k4;
-                            const uint64_t dbh = tc::make_desc_sw128(b1 + kb * V2_BBLK + k4 * 32);
-                            const uint64_t dbl = tc::make_desc_sw128(b1 + (n_kb + kb) * V2_BBLK + k4 * 32);
-                            tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_alo + acol, dbh, IDESC1, (kb | k4) != 0);
-                            tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_ahi + acol, dbl, IDESC1, 1u);
-                            tc::umma_tf32_ts(tm_d1 + 64 * buf, tm_ahi + acol, dbh, IDESC1, 1u);
+                            const uint64_t dbh = db + (uint32_t)((kb * V2_BBLK + k4 * 32) >> 4);
+                            const uint64_t dbl = dbh + lo_off;
+                            tc::umma_tf32_ts(dcol, tm_alo + acol, dbh, IDESC1, (kb | k4) != 0);
+                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbl, IDESC1, 1u);
+                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbh, IDESC1, 1u);
                         }
                     }
                     tc::umma_commit(b1_empty + s1);        // z tile consumed
                     tc::umma_commit(d1_full + buf);        // P ready
                 }
-                if (t > 0) {
-                    const int u = t - 1, ws = u & 1;
-                    tc::mbar_wait(phi_full, u & 1);
+                __syncwarp();
+            }
+            if (t > 0) {
+                const int u = t - 1, ws = u & 1;
+                tc::mbar_wait(phi_full, u & 1);
+                if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u >> 1) & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
                     if (a.do_gemm2) {
-                        tc::mbar_wait(w_full + ws, (u >> 1) & 1);
-                        tc::tc_fence_after();
+                        const uint64_t dw = dW + (uint32_t)((ws * 4 * NG * 128) >> 4);
                         for (int b = 0; b < nb2; ++b)
+#pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                tc::umma_tf32(tm_d2, tc::make_desc_sw128(tc::smem_u32(sPhi + b * V2_BLK) + k4 * 32),
-                                              tc::make_desc_sw128(tc::smem_u32(sW + (ws * 4 + b) * (NG * 128)) + k4 * 32),
-                                              IDESC2, (u | b | k4) != 0);
+                                tc::umma_tf32(tm_d2, dPhi + (uint32_t)((b * V2_BLK + k4 * 32) >> 4),
+                                              dw + (uint32_t)((b * NG * 128 + k4 * 32) >> 4), IDESC2, (u | b | k4) != 0);
                         tc::umma_commit(w_empty + ws);
                     }
                     tc::umma_commit(phi_empty);            // Phi tile consumed by the tensor core (1 of 2 arrivals)
                     if (u == n_my - 1) tc::umma_commit(d2_full);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == V2_EPI_WARPS + 1) {
         // ===================================== TMA PRODUCER =====================================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const int zc = a.zt_cs != 0 ? chain : 0;
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (cs + t * a.CS) * V2_BN;
@@ -292,7 +311,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
         }
     } else {
         // ===================================== STORE WARP =====================================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (cs + t * a.CS) * V2_BN;
                 tc::mbar_wait(phi_full, t & 1);
