@@ -73,6 +73,7 @@ struct LayerWs {
     size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
     int tc2;                                                 // pipelined TC forward: prepped operand buffers below
     int64_t n_zt, n_wt; size_t zt, wt;
+    int64_t n_wp; size_t wp; int bwd2;                       // pipelined TC backward: padded W rows
 };
 struct WsLayout {
     LayerWs L[DGPRF_MAX_LAYERS];
@@ -142,6 +143,12 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         if (mode == DGPRF_MODE_HYPER) {
             s.n_tpart = (int64_t)s.CS * B * layer_d(y); s.tpart = take(s.n_tpart);
             s.n_rpart = (int64_t)s.CS * B;              s.rpart = take(s.n_rpart);
+        }
+        if (mode >= DGPRF_MODE_TRAIN && m->precision == DGPRF_PREC_TF32 &&
+            dgprf_bwd_tc2_shape_ok(B, y.M, y.g, y.d_prev, s.CS, w->RS)) {
+            s.bwd2 = 1;
+            s.n_wp = dgprf_bwd_tc2_wp_floats(layer_F(y));
+            s.wp = take(s.n_wp);
         }
         if (s.tc2) {
             s.n_zt = dgprf_fwd_tc2_zt_floats(y.M);          // one copy per chain (only the first is used when z is shared)
@@ -325,9 +332,11 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         a.Dpart = l > 0 ? wsf(ws, w.L[l].dpart) : nullptr; a.d_cs = w.L[l].n_dpart;
         a.Tpart = hyper ? wsf(ws, w.L[l].tpart) : nullptr; a.t_cs = w.L[l].n_tpart;
         a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
-        int rc = (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc_supported(a))
-                     ? dgprf_launch_bwd_tc(a, m->n_chains, st)
-                     : dgprf_launch_bwd_simt(a, m->n_chains, st);
+        a.wp = w.L[l].bwd2 ? wsf(ws, w.L[l].wp) : nullptr;
+        int rc;
+        if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc2_supported(a)) rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
+        else if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc_supported(a)) rc = dgprf_launch_bwd_tc(a, m->n_chains, st);
+        else rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
         if (rc) return rc;
         if (hyper) {
             HypArgs h;

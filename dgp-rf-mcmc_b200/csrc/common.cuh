@@ -96,6 +96,7 @@ struct BwdArgs {
     float* Dpart;     int64_t d_cs;           // [CS][B][d_prev]  dU/dF_{l-1} partials (nullable)
     float* Tpart;     int64_t t_cs;           // [CS][B][d]       raw T = dP z^T     (hyper)
     float* Rpart;     int64_t r_cs;           // [CS][B]          R = rowsum(dP)     (hyper | mean)
+    float* wp;                                // pipelined TC backward: zero-padded W rows [F][32] (workspace)
 };
 
 // ---- device helpers ----------------------------------------------------------------------

@@ -24,22 +24,6 @@ constexpr int BT_THREADS = 256;
 constexpr int BT_BLK = BT_BM * 128;   // bytes of a [128 x 32 tf32] block
 constexpr uint32_t BT_TMEM_COLS = 256;   // D1: 128 | D2: <= 64 | D3: <= 64
 
-namespace tc {
-// MN-major tf32 descriptor, SWIZZLE_128B_BASE32B (layout type 1): LBO = byte stride between 32-element MN
-// groups, SBO = byte stride between the 4-row K atoms (a tf32 instruction spans K = 8 = two atoms)
-__device__ __forceinline__ uint64_t make_desc_mn_b32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {      // both operands MN-major
-    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
-}
-}  // namespace tc
 
 __device__ float* g_bwd_dbg = nullptr;     // debug dump target (DGPRF_BWD_TC_DEBUG=1)
 
@@ -120,7 +104,7 @@ k2_bwd_tc(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
         for (int rt = rs; rt < n_rt; rt += a.RS) {
             const int row0 = rt * BT_BM;
             // ---- Phi tile: TMA load of the saved features (OOB rows / columns arrive as zeros) ----
-            if (tid == 0) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::mbar_expect_tx(bar_tma, phi_bytes);
                 for (int b = 0; b < 2; ++b) {
                     tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + b * BT_BLK), bar_tma, c0 + 32 * b, row0, chain);
@@ -149,7 +133,7 @@ k2_bwd_tc(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
             }
             tc::fence_async_smem();
             __syncthreads();
-            if (tid == 0) {                                   // MMA-1: dPhi = dF W^T
+            if (warp == 0 && tc::elect_one()) {               // MMA-1: dPhi = dF W^T
                 tc::tc_fence_after();
                 for (int kb = 0; kb < KGB; ++kb) {
                     const int kleft = a.g - 32 * kb;
@@ -216,7 +200,7 @@ k2_bwd_tc(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __
             tc::tc_fence_before();
             tc::fence_async_smem();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::tc_fence_after();
                 // MMA-2: gW_tile += Phi_tile^T dF  (both operands MN-major; K = 128 batch rows, 8 per instruction)
                 for (int k8 = 0; k8 < BT_BM / 8; ++k8)

@@ -1,0 +1,351 @@
+// K2 v2 (tensor-core, DGPRF_PREC_TF32): reverse pass of one [RF layer -> GP layer] pair with every accumulation
+// kept on chip.  Same three UMMAs per (128-row tile, 64-column tile) as k2_bwd_tc.cu,
+//   MMA-1  dPhi = dF . W_tile^T      MMA-2  gW_tile += Phi_tile^T . dF      MMA-3  T += dP . z_tile^T
+// but the CTA (row split rs, column split cs) walks its ROW tiles in the outer loop and its column tiles in the
+// inner loop:
+//   * all gW tiles of the CTA's column tiles stay resident in TENSOR MEMORY for the whole kernel (up to 10 tiles of
+//     32 columns) and are written once, as row-split slab rs, at the end;
+//   * T = dP z^T accumulates in TMEM over the column tiles of a row tile, so the dF_prev slab is written once per
+//     row tile instead of being read-modified-written per column tile;
+//   * the saved-feature tile (64 KB, the HBM stream that bounds this kernel) arrives through a 2-stage TMA ring;
+//     the stage is released as soon as MMA-2 and the dP epilogue have consumed it, so the load of tile t+2 is in
+//     flight during tile t and t+1;
+//   * the W rows and z rows of a column tile are TMA loads too (W from a zero-padded copy [F][32] made by a prep
+//     kernel because a TMA row stride must be a multiple of 16 bytes; z directly from the model's spectral draws).
+// W-only mode, n_gp <= 32, d_prev <= 64; other shapes stay on k2_bwd_tc.cu / the SIMT kernel.
+#include <stdlib.h>
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+constexpr int B2_BM = 128, B2_BN = 64, B2_NG = 32;
+constexpr int B2_THREADS = 256;
+constexpr int B2_BLK = B2_BM * 128;            // bytes of a [128 x 32 tf32] block
+constexpr int B2_HDR = 2048;                   // R_s | s_s | m_s | mbarriers | TMEM slot
+constexpr int B2_MAX_LOC = 10;                 // resident gW tiles: 10 x 32 TMEM columns
+constexpr uint32_t B2_TMEM_COLS = 512;         // D1 128 | D3 64 | D2 320
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
+           const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_z) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* R_s = reinterpret_cast<float*>(sm);                 // [2][128] row sums of dP per column half
+    float* s_s = R_s + 2 * B2_BM;                              // [64] exp(log_inv_ls[q]), q < d_prev
+    float* m_s = s_s + 64;                                     // [64] mean[q]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(m_s + 64);
+    uint64_t* phi_full = bars + 0;    // [2] TMA complete_tx
+    uint64_t* w_full = bars + 2;      // TMA complete_tx
+    uint64_t* z_full = bars + 3;      // TMA complete_tx
+    uint64_t* barA = bars + 4;        // MMA-1 + MMA-2 of a tile complete
+    uint64_t* barB = bars + 5;        // MMA-3 of a tile complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint8_t* sPhi = sm + B2_HDR;                     // 2 stages x 4 blocks: cos 0,1 | sin 2,3   (32-byte-atom swizzle)
+    uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
+    uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
+    uint8_t* sdP = sdF2 + B2_BLK;                    // 2 blocks [128 rows x 32 feature cols]          (A of MMA-3)
+    uint8_t* sW = sdP + 2 * B2_BLK;                  // [128 feature rows x 32 j]                      (B of MMA-1)
+    uint8_t* sZ = sW + B2_BLK;                       // 2 blocks [64 q rows x 32 feature cols]         (B of MMA-3)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chain = blockIdx.z, cs = blockIdx.y, rs = blockIdx.x;
+    const bool rbf = a.kind == DGPRF_KIND_RBF;
+    const float arc_scale = 1.41421356237f * __expf(__ldg(a.log_amp + chain * a.h_cs)) * rsqrtf((float)a.M);
+    const int NQ = a.d_prev > 0 ? ((a.d_prev + 15) & ~15) : 0;      // UMMA N of MMA-3
+    const int zc = a.z_cs != 0 ? chain : 0;
+
+    const int n_ct = (a.M + B2_BN - 1) / B2_BN, n_rt = (a.B + B2_BM - 1) / B2_BM;
+    const int n_loc = cs < n_ct ? (n_ct - cs + a.CS - 1) / a.CS : 0;          // column tiles of this CTA
+    const int n_rloc = rs < n_rt ? (n_rt - rs + a.RS - 1) / a.RS : 0;         // row tiles of this CTA
+    const int T = n_loc * n_rloc;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, B2_TMEM_COLS);
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) tc::mbar_init(bars + i, 1);
+        tc::mbar_fence_init();
+    }
+    if (tid < 64) {
+        const bool ok = tid < a.d_prev;
+        s_s[tid] = ok ? expf(__ldg(a.log_inv_ls + chain * a.h_cs + tid)) : 0.f;
+        m_s[tid] = (ok && a.has_mean) ? __ldg(a.mean + chain * a.h_cs + tid) : 0.f;
+    }
+    if (!rbf) {       // arc-cosine: the sin halves of the Phi stages and of the W tile are never loaded; keep them finite
+        for (int e = tid; e < (2 * 4 * B2_BLK) / 16; e += B2_THREADS) reinterpret_cast<float4*>(sPhi)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = tid; e < B2_BLK / 16; e += B2_THREADS) reinterpret_cast<float4*>(sW)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tc::fence_async_smem();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_d1 = tmem_base, tm_d3 = tmem_base + 128, tm_d2 = tmem_base + 192;
+
+    constexpr uint32_t IDESC1 = tc::make_idesc_tf32(B2_BM, 2 * B2_BN);
+    constexpr uint32_t IDESC2 = tc::make_idesc_tf32_mn(B2_BM, B2_NG);
+    const uint32_t IDESC3 = tc::make_idesc_tf32(B2_BM, NQ > 0 ? NQ : 16);
+    const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
+
+    // tile k of this CTA = (row tile k / n_loc, column tile k % n_loc); the loaders run on one elected thread
+    auto load_phi = [&](int k) {
+        const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
+        tc::mbar_expect_tx(phi_full + s, phi_bytes);
+        for (int b = 0; b < 2; ++b) {
+            tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+            if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+        }
+    };
+    auto load_w = [&](int k) {
+        const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+        tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
+        tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
+        if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
+    };
+    auto load_z = [&](int k) {
+        const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+        tc::mbar_expect_tx(z_full, 2u * NQ * 128);
+        for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 0, zc);
+    };
+    if (warp == 0 && T > 0 && tc::elect_one()) {
+        load_phi(0);
+        if (T > 1) load_phi(1);
+        load_w(0);
+        if (NQ > 0) load_z(0);
+    }
+
+    const uint64_t d_dF = tc::make_desc_sw128(tc::smem_u32(sdF));
+    const uint64_t d_W = tc::make_desc_sw128(tc::smem_u32(sW));
+    const uint64_t d_dP = tc::make_desc_sw128(tc::smem_u32(sdP));
+    const uint64_t d_Z = tc::make_desc_sw128(tc::smem_u32(sZ));
+    const uint64_t d_dF2 = tc::make_desc_mn_b32(tc::smem_u32(sdF2), B2_BLK, 512);
+    const uint64_t d_Phi = tc::make_desc_mn_b32(tc::smem_u32(sPhi), B2_BLK, 512);
+    const int k1steps = (a.g + 7) / 8;
+
+    const int lq = warp & 3, hh = warp >> 2;             // TMEM lane quarter, 32-column half of the tile
+    const int r = 32 * lq + lane;
+    float rsum = 0.f;
+
+    for (int k = 0; k < T; ++k) {
+        const int il = k % n_loc, rl = k / n_loc;
+        const int row0 = (rs + rl * a.RS) * B2_BM;
+        const int s = k & 1;
+        if (il == 0) {
+            // ---- dF tile of this row tile (A of MMA-1, B of MMA-2); every MMA that read the old one has completed ----
+            constexpr int NE = B2_BM * 32 / B2_THREADS;
+            float v[NE];
+#pragma unroll
+            for (int u = 0; u < NE; ++u) {
+                const int e = tid + u * B2_THREADS;
+                const int rr = e >> 5, j = e & 31;
+                const int64_t row = row0 + rr;
+                v[u] = (row < a.B && j < a.g) ? slab_load(a.dF, chain, row, j) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < NE; ++u) {
+                const int e = tid + u * B2_THREADS;
+                const int rr = e >> 5, j = e & 31;
+                const float t = tc::to_tf32(v[u]);
+                *reinterpret_cast<float*>(sdF + tc::sw128_off(rr, j)) = t;
+                *reinterpret_cast<float*>(sdF2 + tc::sw128b32_off(rr, j)) = t;
+            }
+            tc::fence_async_smem();
+            __syncthreads();
+            rsum = 0.f;
+        }
+        // ---- MMA-1 (dPhi -> D1) and MMA-2 (gW tile il, accumulated over the row tiles) ----
+        if (warp == 0) {
+            tc::mbar_wait(phi_full + s, (k >> 1) & 1);
+            tc::mbar_wait(w_full, k & 1);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                for (int k4 = 0; k4 < k1steps; ++k4)
+                    tc::umma_tf32(tm_d1, d_dF + 2 * k4, d_W + 2 * k4, IDESC1, k4 != 0);
+                const uint64_t dphi = d_Phi + (uint32_t)((s * 4 * B2_BLK) >> 4);
+#pragma unroll 4
+                for (int k8 = 0; k8 < B2_BM / 8; ++k8)
+                    tc::umma_tf32(tm_d2 + il * B2_NG, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, (rl | k8) != 0);
+                tc::umma_commit(barA);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(barA, k & 1);
+        tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is also read by every thread below
+        tc::tc_fence_after();
+        if (warp == 0) {
+            // the tensor pipe is in order: MMA-1(k) done => W tile free; MMA-3(k-1) done => z tile and dP tile free
+            if (tc::elect_one()) {
+                if (k + 1 < T) load_w(k + 1);
+                if (NQ > 0 && k > 0) load_z(k);
+            }
+            __syncwarp();
+        }
+        // ---- epilogue 1: dP from dPhi (TMEM) and the Phi tile (smem) -> dP tile (A of MMA-3), row sums ----
+        {
+            const uint8_t* ph = sPhi + s * 4 * B2_BLK;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float dc[16], ds[16];
+                const uint32_t lane_addr = (uint32_t)(32 * lq) << 16;
+                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh + 16 * pass, dc);
+                if (rbf) tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh + 16 * pass, ds);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int cc = 4 * pass + c4;                // 16-byte chunk inside the 32-wide block
+                    const float4 pc = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc));
+                    float4 o;
+                    if (rbf) {
+                        const float4 ps = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc));
+                        o.x = pc.x * ds[4 * c4 + 0] - ps.x * dc[4 * c4 + 0];
+                        o.y = pc.y * ds[4 * c4 + 1] - ps.y * dc[4 * c4 + 1];
+                        o.z = pc.z * ds[4 * c4 + 2] - ps.z * dc[4 * c4 + 2];
+                        o.w = pc.w * ds[4 * c4 + 3] - ps.w * dc[4 * c4 + 3];
+                    } else {
+                        o.x = pc.x > 0.f ? dc[4 * c4 + 0] * arc_scale : 0.f;
+                        o.y = pc.y > 0.f ? dc[4 * c4 + 1] * arc_scale : 0.f;
+                        o.z = pc.z > 0.f ? dc[4 * c4 + 2] * arc_scale : 0.f;
+                        o.w = pc.w > 0.f ? dc[4 * c4 + 3] * arc_scale : 0.f;
+                    }
+                    rsum += (o.x + o.y) + (o.z + o.w);
+                    o.x = tc::to_tf32(o.x); o.y = tc::to_tf32(o.y); o.z = tc::to_tf32(o.z); o.w = tc::to_tf32(o.w);
+                    *reinterpret_cast<float4*>(sdP + hh * B2_BLK + tc::sw128_chunk(r, cc)) = o;
+                }
+            }
+        }
+        tc::tc_fence_before();
+        tc::fence_async_smem();
+        __syncthreads();
+        // ---- stage s is free (MMA-2 complete, every thread has read it): prefetch tile k+2; then MMA-3 ----
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                if (k + 2 < T) load_phi(k + 2);
+                if (NQ > 0) {
+                    tc::mbar_wait(z_full, k & 1);
+                    tc::tc_fence_after();
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::umma_tf32(tm_d3, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
+                                          d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3, (il | b | k4) != 0);
+                }
+                tc::umma_commit(barB);
+            }
+            __syncwarp();
+        }
+        if (il == n_loc - 1) {
+            // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
+            R_s[hh * B2_BM + r] = rsum;
+            tc::mbar_wait(barB, k & 1);
+            tc::tc_fence_after();
+            __syncthreads();
+            if (NQ > 0 && warp < 4 && a.Dpart != nullptr) {
+                const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
+                const float Rr = R_s[r] + R_s[B2_BM + r];
+                for (int qc = 0; qc < NQ / 16; ++qc) {
+                    float t[16];
+                    tc::tmem_ld16(tm_d3 + ((uint32_t)(32 * warp) << 16) + 16 * qc, t);
+                    tc::tmem_ld_wait();
+                    if (row < a.B) {
+                        float* dst = a.Dpart + chain * a.d_cs + ((int64_t)cs * a.B + row) * a.d_prev;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int q = 16 * qc + i;
+                            if (q < a.d_prev) {
+                                float v = s_s[q] * t[i];
+                                if (a.has_mean) v = fmaf(m_s[q], Rr, v);
+                                dst[q] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+        }
+    }
+
+    // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp < 4) {
+        const int fl = 32 * warp + lane;                               // feature row inside [cos 64 | sin 64]
+        for (int i = 0; i < n_loc; ++i) {
+            const int c0 = (cs + i * a.CS) * B2_BN;
+            const int col = c0 + (fl & (B2_BN - 1));
+            const bool live = col < a.M && (rbf || fl < B2_BN);
+            const int64_t frow = (fl >= B2_BN ? a.M : 0) + col;
+            float* dst = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss + frow * a.g;
+#pragma unroll
+            for (int c16 = 0; c16 < B2_NG / 16; ++c16) {
+                float v[16];
+                tc::tmem_ld16(tm_d2 + i * B2_NG + ((uint32_t)(32 * warp) << 16) + 16 * c16, v);
+                tc::tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (16 * c16 + j < a.g) dst[16 * c16 + j] = T > 0 ? v[j] : 0.f;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, B2_TMEM_COLS);
+}
+
+// W [F, g] -> wp [F][32]: zero-padded, tf32-rounded rows (a TMA row stride must be a multiple of 16 bytes)
+__global__ void __launch_bounds__(256)
+k_prep_bwd_tc2(const float* __restrict__ W, int64_t w_cs, int F, int g, float* __restrict__ wp) {
+    const int chain = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)F * B2_NG) return;
+    const int64_t f = i >> 5;
+    const int j = (int)(i & 31);
+    wp[(int64_t)chain * F * B2_NG + i] = j < g ? tc::to_tf32(__ldg(W + chain * w_cs + f * g + j)) : 0.f;
+}
+
+static constexpr size_t kB2Smem = 1024 + B2_HDR + 8 * (size_t)B2_BLK + 2 * (size_t)B2_BLK + 2 * (size_t)B2_BLK +
+                                  (size_t)B2_BLK + 2 * 64 * 128;
+
+bool dgprf_bwd_tc2_shape_ok(int B, int M, int g, int d_prev, int CS, int RS) {
+    const int n_ct = ceil_div(M, B2_BN), n_rt = ceil_div(B, B2_BM);
+    return (M % 4) == 0 && g <= B2_NG && d_prev <= 64 && CS <= n_ct && RS <= n_rt && ceil_div(n_ct, CS) <= B2_MAX_LOC &&
+           getenv("DGPRF_NO_TC2") == nullptr;
+}
+int64_t dgprf_bwd_tc2_wp_floats(int F) { return (int64_t)F * B2_NG; }
+
+bool dgprf_bwd_tc2_supported(const BwdArgs& a) {
+    return !a.hyper && a.wp != nullptr && (a.phi_cs % 4) == 0 && dgprf_bwd_tc2_shape_ok(a.B, a.M, a.g, a.d_prev, a.CS, a.RS);
+}
+
+int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
+    static_assert(kB2Smem <= 232448, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k2_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
+        configured = true;
+    }
+    {
+        ProfScope _ps("k_prep_bwd_tc2", st);
+        k_prep_bwd_tc2<<<dim3(ceil_div(a.F * B2_NG, 256), n_chains), 256, 0, st>>>(a.W, a.w_cs, a.F, a.g, a.wp);
+        DGPRF_CHECK_CUDA(cudaGetLastError());
+    }
+    CUtensorMap mc, ms, mw, mz;
+    memset(&ms, 0, sizeof(ms));
+    memset(&mz, 0, sizeof(mz));
+    int rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
+    if (rc) return rc;
+    if (a.kind == DGPRF_KIND_RBF) {
+        rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
+        if (rc) return rc;
+    }
+    rc = dgprf_make_tmap_3d(&mw, a.wp, B2_NG, a.F, n_chains, B2_NG, (uint64_t)a.F * B2_NG, B2_BN);
+    if (rc) return rc;
+    if (a.d_prev > 0) {
+        const int NQ = (a.d_prev + 15) & ~15;
+        rc = dgprf_make_tmap_3d(&mz, a.z, a.M, a.d, a.z_cs != 0 ? n_chains : 1, a.M, a.z_cs, NQ);
+        if (rc) return rc;
+    }
+    dim3 grid(a.RS, a.CS, n_chains);
+    { ProfScope _ps("k2_bwd_tc2", st); k2_bwd_tc2<<<grid, B2_THREADS, kB2Smem, st>>>(a, mc, ms, mw, mz); }
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
+}

@@ -47,6 +47,10 @@ int64_t dgprf_fwd_tc2_wt_floats(int F, int g);
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
+bool dgprf_bwd_tc2_shape_ok(int B, int M, int g, int d_prev, int CS, int RS);
+int64_t dgprf_bwd_tc2_wp_floats(int F);
+bool dgprf_bwd_tc2_supported(const BwdArgs& a);
+int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_bwd_tc_supported(const BwdArgs& a);
 int dgprf_launch_bwd_tc(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_bwd_simt(const BwdArgs& a, int n_chains, cudaStream_t st);

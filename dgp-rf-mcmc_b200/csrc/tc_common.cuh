@@ -53,6 +53,21 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// MN-major tf32 descriptor, SWIZZLE_128B_BASE32B (layout type 1): LBO = byte stride between 32-element MN
+// groups, SBO = byte stride between the 4-row K atoms (a tf32 instruction spans K = 8 = two atoms)
+__device__ __forceinline__ uint64_t make_desc_mn_b32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {      // both operands MN-major
+    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -119,6 +134,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (done) return;
         if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 2 GHz
     }
+}
+
+// one lane of a CONVERGED warp; tells the compiler the guarded region is single-threaded, so the uniform-datapath
+// tcgen05 instructions inside are issued without a per-lane uniformity loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- TMA -----------------------------------------------------------------------------------------
