@@ -36,9 +36,10 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     uint64_t* phi_full = bars + 0;    // [2] TMA complete_tx
     uint64_t* w_full = bars + 2;      // TMA complete_tx
     uint64_t* z_full = bars + 3;      // TMA complete_tx
-    uint64_t* barA = bars + 4;        // MMA-1 + MMA-2 of a tile complete
+    uint64_t* barA = bars + 4;        // MMA-1 of a tile complete (dPhi ready)
     uint64_t* barB = bars + 5;        // MMA-3 of a tile complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* barC = bars + 6;        // MMA-2 of a tile complete (Phi stage and dF tile consumed)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
     uint8_t* sPhi = sm + B2_HDR;                     // 2 stages x 4 blocks: cos 0,1 | sin 2,3   (32-byte-atom swizzle)
     uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
     uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
@@ -60,7 +61,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, B2_TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < 6; ++i) tc::mbar_init(bars + i, 1);
+        for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
         tc::mbar_fence_init();
     }
     if (tid < 64) {
@@ -123,51 +124,69 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const int r = 32 * lq + lane;
     float rsum = 0.f;
 
-    for (int k = 0; k < T; ++k) {
-        const int il = k % n_loc, rl = k / n_loc;
-        const int row0 = (rs + rl * a.RS) * B2_BM;
-        const int s = k & 1;
-        if (il == 0) {
-            // ---- dF tile of this row tile (A of MMA-1, B of MMA-2); every MMA that read the old one has completed ----
-            constexpr int NE = B2_BM * 32 / B2_THREADS;
-            float v[NE];
+    // dF tile of a row tile (A of MMA-1, B of MMA-2): the partial slabs are summed in slab order (the order of
+    // slab_load), one slab per pass so that a thread keeps 16 independent loads in flight
+    auto stage_dF = [&](int row0) {
+        constexpr int NE = B2_BM * 32 / B2_THREADS;
+        float v[NE];
+        const float* base = a.dF.ptr + chain * a.dF.cs;
+#pragma unroll
+        for (int u = 0; u < NE; ++u) v[u] = 0.f;
+        for (int sl = 0; sl < a.dF.n_slabs; ++sl) {
+            const float* p = base + sl * a.dF.ss;
 #pragma unroll
             for (int u = 0; u < NE; ++u) {
                 const int e = tid + u * B2_THREADS;
                 const int rr = e >> 5, j = e & 31;
                 const int64_t row = row0 + rr;
-                v[u] = (row < a.B && j < a.g) ? slab_load(a.dF, chain, row, j) : 0.f;
+                const float x = (row < a.B && j < a.g) ? __ldg(p + row * a.dF.ld + j) : 0.f;
+                v[u] = sl == 0 ? x : v[u] + x;
             }
-#pragma unroll
-            for (int u = 0; u < NE; ++u) {
-                const int e = tid + u * B2_THREADS;
-                const int rr = e >> 5, j = e & 31;
-                const float t = tc::to_tf32(v[u]);
-                *reinterpret_cast<float*>(sdF + tc::sw128_off(rr, j)) = t;
-                *reinterpret_cast<float*>(sdF2 + tc::sw128b32_off(rr, j)) = t;
-            }
-            tc::fence_async_smem();
-            __syncthreads();
-            rsum = 0.f;
         }
-        // ---- MMA-1 (dPhi -> D1) and MMA-2 (gW tile il, accumulated over the row tiles) ----
-        if (warp == 0) {
-            tc::mbar_wait(phi_full + s, (k >> 1) & 1);
-            tc::mbar_wait(w_full, k & 1);
-            tc::tc_fence_after();
-            if (tc::elect_one()) {
-                for (int k4 = 0; k4 < k1steps; ++k4)
-                    tc::umma_tf32(tm_d1, d_dF + 2 * k4, d_W + 2 * k4, IDESC1, k4 != 0);
-                const uint64_t dphi = d_Phi + (uint32_t)((s * 4 * B2_BLK) >> 4);
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+            const int e = tid + u * B2_THREADS;
+            const int rr = e >> 5, j = e & 31;
+            const float t = tc::to_tf32(v[u]);
+            *reinterpret_cast<float*>(sdF + tc::sw128_off(rr, j)) = t;
+            *reinterpret_cast<float*>(sdF2 + tc::sw128b32_off(rr, j)) = t;
+        }
+        tc::fence_async_smem();
+    };
+    // MMA-1 (dPhi -> D1; barA) then MMA-2 (gW tile il += Phi^T dF, accumulated over the row tiles; barC) of tile k.
+    // Runs on the elected thread.  Only MMA-1 is on the critical path of the dP epilogue.
+    auto issue_mma12 = [&](int k) {
+        const int s = k & 1, il = k % n_loc, rl = k / n_loc;
+        tc::mbar_wait(w_full, k & 1);
+        tc::tc_fence_after();
+        for (int k4 = 0; k4 < k1steps; ++k4)
+            tc::umma_tf32(tm_d1, d_dF + 2 * k4, d_W + 2 * k4, IDESC1, k4 != 0);
+        tc::umma_commit(barA);
+        tc::mbar_wait(phi_full + s, (k >> 1) & 1);
+        tc::tc_fence_after();
+        const uint64_t dphi = d_Phi + (uint32_t)((s * 4 * B2_BLK) >> 4);
 #pragma unroll 4
-                for (int k8 = 0; k8 < B2_BM / 8; ++k8)
-                    tc::umma_tf32(tm_d2 + il * B2_NG, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, (rl | k8) != 0);
-                tc::umma_commit(barA);
-            }
+        for (int k8 = 0; k8 < B2_BM / 8; ++k8)
+            tc::umma_tf32(tm_d2 + il * B2_NG, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, (rl | k8) != 0);
+        tc::umma_commit(barC);
+    };
+
+    if (T > 0) {
+        stage_dF(rs * B2_BM);
+        __syncthreads();
+        if (warp == 0) {
+            if (tc::elect_one()) issue_mma12(0);
             __syncwarp();
         }
-        tc::mbar_wait(barA, k & 1);
-        tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is also read by every thread below
+    }
+
+    for (int k = 0; k < T; ++k) {
+        const int il = k % n_loc, rl = k / n_loc;
+        const int row0 = (rs + rl * a.RS) * B2_BM;
+        const int s = k & 1;
+        const bool row_end = il == n_loc - 1;
+        tc::mbar_wait(barA, k & 1);                       // dPhi of tile k is in D1
+        tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is read by every thread below
         tc::tc_fence_after();
         if (warp == 0) {
             // the tensor pipe is in order: MMA-1(k) done => W tile free; MMA-3(k-1) done => z tile and dP tile free
@@ -177,9 +196,24 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             }
             __syncwarp();
         }
-        // ---- epilogue 1: dP from dPhi (TMEM) and the Phi tile (smem) -> dP tile (A of MMA-3), row sums ----
+        // ---- epilogue 1: dP from dPhi (TMEM) and the Phi tile (smem) -> dP tile (A of MMA-3), row sums.
+        //      The thread's Phi values go to registers first so the ring stage can be refilled right away. ----
         {
             const uint8_t* ph = sPhi + s * 4 * B2_BLK;
+            float4 pcv[8], psv[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                pcv[cc] = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc));
+                if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc));
+            }
+            __syncthreads();
+            if (warp == 0) {          // every thread has read stage s; once MMA-2(k) is done too, prefetch tile k+2
+                if (k + 2 < T && tc::elect_one()) {
+                    tc::mbar_wait(barC, k & 1);
+                    load_phi(k + 2);
+                }
+                __syncwarp();
+            }
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 float dc[16], ds[16];
@@ -190,10 +224,10 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int cc = 4 * pass + c4;                // 16-byte chunk inside the 32-wide block
-                    const float4 pc = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc));
+                    const float4 pc = pcv[cc];
                     float4 o;
                     if (rbf) {
-                        const float4 ps = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc));
+                        const float4 ps = psv[cc];
                         o.x = pc.x * ds[4 * c4 + 0] - ps.x * dc[4 * c4 + 0];
                         o.y = pc.y * ds[4 * c4 + 1] - ps.y * dc[4 * c4 + 1];
                         o.z = pc.z * ds[4 * c4 + 2] - ps.z * dc[4 * c4 + 2];
@@ -210,13 +244,14 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 }
             }
         }
+        if (row_end) R_s[hh * B2_BM + r] = rsum;
         tc::tc_fence_before();
         tc::fence_async_smem();
         __syncthreads();
-        // ---- stage s is free (MMA-2 complete, every thread has read it): prefetch tile k+2; then MMA-3 ----
+        // ---- MMA-3 (T += dP z^T); inside a row tile MMA-1/2 of the next tile follow at once ----
         if (warp == 0) {
             if (tc::elect_one()) {
-                if (k + 2 < T) load_phi(k + 2);
+                tc::tc_fence_after();
                 if (NQ > 0) {
                     tc::mbar_wait(z_full, k & 1);
                     tc::tc_fence_after();
@@ -227,15 +262,14 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                                           d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3, (il | b | k4) != 0);
                 }
                 tc::umma_commit(barB);
+                if (!row_end && k + 1 < T) issue_mma12(k + 1);
             }
             __syncwarp();
         }
-        if (il == n_loc - 1) {
+        if (row_end) {
             // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
-            R_s[hh * B2_BM + r] = rsum;
             tc::mbar_wait(barB, k & 1);
             tc::tc_fence_after();
-            __syncthreads();
             if (NQ > 0 && warp < 4 && a.Dpart != nullptr) {
                 const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
                 const float Rr = R_s[r] + R_s[B2_BM + r];
@@ -257,9 +291,22 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                     }
                 }
             }
-            tc::tc_fence_before();
+            rsum = 0.f;
+            if (k + 1 < T) {
+                // next row tile: its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
+                tc::mbar_wait(barC, k & 1);
+                stage_dF((rs + (rl + 1) * a.RS) * B2_BM);
+                tc::tc_fence_before();
+                __syncthreads();
+                if (warp == 0) {
+                    if (tc::elect_one()) { tc::tc_fence_after(); issue_mma12(k + 1); }
+                    __syncwarp();
+                }
+            }
         }
     }
+    if (T > 0) tc::mbar_wait(barC, (T - 1) & 1);           // the last MMA-2: every gW tile is final
+    tc::tc_fence_after();
 
     // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
     tc::tc_fence_before();
