@@ -80,7 +80,8 @@ struct WsLayout {
     int RS;        // row splits of the layered backward (gW slabs)
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
-    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, total;
+    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, total;
+    int64_t n_dfsum;
 };
 
 static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
@@ -180,6 +181,9 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         off += 256;
     }
     if (mode == DGPRF_MODE_HYPER) w->ghyp = take(w->h_len);
+    for (int l = 0; l + 1 < m->n_layers; ++l)          // pre-summed dF of a pipelined TC backward (one slab instead of CS)
+        if (w->L[l].bwd2 && (int64_t)B * m->layer[l].g > w->n_dfsum) w->n_dfsum = (int64_t)B * m->layer[l].g;
+    if (w->n_dfsum > 0) w->dfsum = take(w->n_dfsum);
     w->total = off;
     return DGPRF_OK;
 }
@@ -334,7 +338,15 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
         a.wp = w.L[l].bwd2 ? wsf(ws, w.L[l].wp) : nullptr;
         int rc;
-        if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc2_supported(a)) rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
+        if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc2_supported(a)) {
+            if (a.dF.n_slabs > 1) {
+                // every column-split CTA reads the whole dF tile: sum the partial slabs once instead of CS times
+                rc = dgprf_launch_sum_slabs(a.dF, B, y.g, wsf(ws, w.dfsum), w.n_dfsum, m->n_chains, st);
+                if (rc) return rc;
+                a.dF.ptr = wsf(ws, w.dfsum); a.dF.cs = w.n_dfsum; a.dF.ss = 0; a.dF.n_slabs = 1;
+            }
+            rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
+        }
         else if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc_supported(a)) rc = dgprf_launch_bwd_tc(a, m->n_chains, st);
         else rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
         if (rc) return rc;

@@ -47,6 +47,12 @@ for name, c in CFGS.items():
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / n
         assert torch.isfinite(ens.engine.theta_w).all()
+        if os.environ.get("DGPRF_BREAKDOWN"):          # per-kernel GPU times of one step (C-ABI profile hook)
+            from dgprf import _ffi
+            _ffi.profile_start()
+            ens.sgmcmc_update(X, Y, c["N"], **kw)
+            for nm, t in _ffi.profile_stop():
+                print(f"    {nm:24s} {t * 1e3:9.1f} us")
         out[f"{name} [{prec}]"] = {"ms_per_step": round(ms, 4), "chain_it_per_s": round(c["C"] * 1e3 / ms, 1),
                                    "algorithmic_TFLOPs": round(c["C"] * flops(c) / ms / 1e9, 2), "GFLOP_per_chain_step": round(flops(c) / 1e9, 3)}
         print(f"{name} [{prec}]: {ms:.4f} ms/step  {c['C'] * 1e3 / ms:.1f} chain-it/s  {c['C'] * flops(c) / ms / 1e9:.2f} TFLOP/s", flush=True)
