@@ -313,6 +313,50 @@ def run_ours(args, rank, world):
         k5_gbs = 20.0 * Cn * n_big / (k5_ms * 1e-3) / 1e9
         del th, mo, gr
 
+
+        # ---- tensor-core kernels at configs[4] layer scale (tf32 mode): the GEMM rooflines ------------------
+        # One [RF -> GP] layer, B=65536 rows, input width 120, M=4096 features, n_gp=30: forward (3xTF32 phase
+        # GEMM + sincos epilogue + Phi.W, saved features stored by TMA) and backward (three tf32 UMMAs per tile,
+        # saved features streamed back by TMA).  Kernel times from the library's CUDA-event hook.
+        from dgprf.engine import Engine, ModelSpec
+        tB, td, tM, tg = 65536, 120, 4096, 30
+        tspec = ModelSpec.build(td, tg, [tM], [tg], ["RBF"], False, False, "gaussian")
+        te = Engine(tspec, 1, precision=_ffi.PREC_TF32)
+        te.theta_w.normal_()
+        te.theta_h[:, te.layout.off_lik_log_var] = -2.0
+        tX = torch.randn(tB, td, device=dev); tY = torch.randn(tB, tg, device=dev)
+        for _ in range(3):
+            te.gradients(tX, tY, 1e5, hyper=False, prior_w=True, prior_h=False)
+        torch.cuda.synchronize()
+        _ffi.profile_start()
+        TREP = 5
+        for _ in range(TREP):
+            te.gradients(tX, tY, 1e5, hyper=False, prior_w=True, prior_h=False)
+        tper = {}
+        for nm, ms in _ffi.profile_stop():
+            tper.setdefault(nm, []).append(ms)
+        tF = 2 * tM
+        phi_bytes = 4.0 * tB * tF
+
+        def tc_entry(name, alg_flops, exe_flops, what):
+            if name not in tper:
+                return None
+            us = 1e3 * statistics.mean(tper[name])
+            return {"kernel": name, "what": what, "avg_us": us,
+                    "algorithmic_tflops": alg_flops / us / 1e6, "executed_tensor_tflops": exe_flops / us / 1e6,
+                    "tensor_frac_executed": exe_flops / us / 1e6 / tf32_peak,
+                    "saved_feature_gbs": phi_bytes / us / 1e3, "hbm_frac": phi_bytes / us / 1e3 / pk["hbm_gbs"]}
+        tc_layer = {
+            "workload": f"one [RF->GP] layer at configs[4] scale: B={tB}, d={td}, M={tM}, n_gp={tg}, RBF, tf32 mode",
+            "tf32_peak_tflops": tf32_peak, "hbm_peak_gbs": pk["hbm_gbs"], "peak_source": pk_src,
+            "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * td * tM + tF * tg),
+                            "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored (TMA)"),
+            "bwd": tc_entry("k2_bwd_tc2", 4.0 * tB * tF * tg, 4.0 * tB * tF * 32,
+                            "dPhi = dF.W^T, gW += Phi^T.dF (accumulators resident in TMEM); Phi loaded (TMA ring)"),
+        }
+        del te, tX, tY
+        torch.cuda.empty_cache()
+
         # ---- 8 independent chains batched per launch (configs[3]'s pattern on this workload) ------------
         from dgprf.chains import ChainEnsemble
         CH = 8
@@ -344,7 +388,7 @@ def run_ours(args, rank, world):
             "dtype": "f32", "data": "synthetic",
             "config": dict(CFG, l2="flushed between timed steps (256 MiB write); per-step CUDA events",
                            precision=("fp32: one cooperative row-fused step kernel per iteration (8-row groups through all layers, update behind a grid barrier)" if args.precision == "fp32" else
-                                      "tf32 tcgen05 forward (3xTF32 phase GEMM, tf32 Phi*W), fp32 SIMT backward"), parallelism=f"{world} independent chain(s), 1 per GPU"),
+                                      "tf32: tcgen05 forward (3xTF32 phase GEMM, tf32 Phi*W) and tcgen05 backward, layered launches"), parallelism=f"{world} independent chain(s), 1 per GPU"),
             "posterior_samples_per_second": it_s / (50 * nb),
             "samples_note": f"cycle = 50 epochs x {nb} it (SURVEY 8d); excludes the per-sample test-set eval",
             "warm_loop": {"value": world * K / t_warm, "unit": UNIT, "note": "back-to-back steps, no L2 flush, CPU launch cost included"},
@@ -358,6 +402,7 @@ def run_ours(args, rank, world):
                                    "frac": k5_gbs / pk["hbm_gbs"], "ms": k5_ms, "bytes": 20.0 * Cn * n_big,
                                    "peak_source": pk_src},
             "multi_chain": multi_chain,
+            "roofline_tc_layer": tc_layer,
             "cpu_baseline": {"value": cpu_its, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_done} minibatch steps of the same workload in {cpu_dt:.1f} s"},
             "clocks": clk,
