@@ -134,6 +134,8 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bo
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// all but the newest committed group of this thread are complete
+__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // sin/cos with a 2-constant Cody-Waite reduction to [-pi, pi] followed by the MUFU
 // approximations (abs error ~5e-7 on the reduced range).  Random-feature phases reach

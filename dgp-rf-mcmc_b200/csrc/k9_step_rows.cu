@@ -34,7 +34,7 @@ struct StepRowsLayer {
 };
 
 struct StepRowsArgs {
-    int32_t n_layers, likelihood, B, d_in, d_out, dmax, Fmax, bs_cap, prefetch_w;
+    int32_t n_layers, likelihood, B, d_in, d_out, dmax, Fmax, bs_cap, prefetch_w, zr_cap;
     int64_t h_cs, w_cs;
     const float* X; int64_t x_cs;
     const float* Y; int64_t y_cs;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void stage_z_rows(float* bs, int ld, const float* z, 
 template <int NQ, bool WMODE>
 __device__ __forceinline__ void small_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bg, int64_t ldb,
                                            int K, int N, bool extra_ones, float* __restrict__ bs, int bs_cap,
-                                           bool first_chunk_staged, float* __restrict__ red, float* __restrict__ out_t) {
+                                           bool first_chunk_staged, bool keep_newest, float* __restrict__ red, float* __restrict__ out_t) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, c4 = lane & 3;
     float acc[NQ][2], ones = 0.f;                            // two independent FMA chains per column
@@ -118,8 +118,12 @@ __device__ __forceinline__ void small_gemm(const float* __restrict__ A, int lda,
             if (WMODE) stage_W_rows(bs, Bg, k0, kc, kp, N);
             else stage_z_rows(bs, ldbs, Bg, ldb, k0, kc, kp, N);
             cp_async_commit();
+            cp_async_wait_all();
+        } else if (keep_newest) {
+            cp_async_wait_but_newest();           // a prefetch for a LATER phase was committed after this operand
+        } else {
+            cp_async_wait_all();
         }
-        cp_async_wait_all();
         __syncthreads();
         const float* Ar = A + r * lda + k0;
 #pragma unroll 2
@@ -166,12 +170,92 @@ __device__ __forceinline__ void small_gemm(const float* __restrict__ A, int lda,
 
 template <bool WMODE>
 __device__ __forceinline__ void small_gemm_dispatch(const float* A, int lda, const float* Bg, int64_t ldb, int K, int N,
-                                                    bool extra_ones, float* bs, int bs_cap, bool staged, float* red, float* out_t) {
+                                                    bool extra_ones, float* bs, int bs_cap, bool staged, bool keep_newest,
+                                                    float* red, float* out_t) {
     const int nq = (N + 3) >> 2;
-    if (nq <= 1) small_gemm<1, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, red, out_t);
-    else if (nq <= 3) small_gemm<3, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, red, out_t);
-    else if (nq <= 8) small_gemm<8, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, red, out_t);
-    else small_gemm<16, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, red, out_t);
+    if (nq <= 1) small_gemm<1, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, keep_newest, red, out_t);
+    else if (nq <= 3) small_gemm<3, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, keep_newest, red, out_t);
+    else if (nq <= 8) small_gemm<8, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, keep_newest, red, out_t);
+    else small_gemm<16, WMODE>(A, lda, Bg, ldb, K, N, extra_ones, bs, bs_cap, staged, keep_newest, red, out_t);
+}
+// Stage chunk 0 of the z-row operand of small_gemm<.., false> ahead of time (same layout computation); returns
+// whether the whole operand is that one chunk (only then may the caller pass first_chunk_staged = true).
+__device__ __forceinline__ bool small_gemm_prefetch_z(const float* Bg, int64_t ldb, int K, int N, float* bs, int bs_cap) {
+    const int K4 = (K + 3) & ~3;
+    const int kc_max = min(K4, ((bs_cap / N) - 4) & ~3);
+    if (kc_max < K4) return false;
+    stage_z_rows(bs, kc_max + 4, Bg, ldb, 0, K, K4, N);
+    return true;
+}
+
+// out_t[n][r] = sum_k Phi[r][k] W[k][n] with the WHOLE W (natural layout, rows >= K zero-filled up to K4) staged in
+// `bs` and the output width N a compile-time constant: four consecutive W rows are N contiguous float4, so a lane
+// reads them with N 128-bit loads and knows at compile time which (k, n) every component is.  lane = (row pair
+// rp = lane / 8, k-slot ks = lane % 8): 2 rows x N columns x 4 k per step = 8N FMAs for N + 2 shared loads
+// (the generic small_gemm issues 13 loads per 12 FMAs).  Reduction: shuffles over the 8 k-slots, then the same
+// fixed-order cross-warp sum as small_gemm.
+template <int N>
+__device__ __forceinline__ void phi_w_gemm(const float* __restrict__ A, int lda, int K, const float* __restrict__ bs,
+                                           float* __restrict__ red, float* __restrict__ out_t) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rp = lane >> 3, ks = lane & 7;
+    float acc0[N], acc1[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc0[n] = acc1[n] = 0.f;
+    const int n4 = ((K + 3) & ~3) >> 2;                     // float4 steps along K
+    const float* A0 = A + (2 * rp) * lda;
+    const float* A1 = A0 + lda;
+    for (int k4 = warp * 8 + ks; k4 < n4; k4 += kSW * 8) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A0 + 4 * k4);
+        const float4 a1 = *reinterpret_cast<const float4*>(A1 + 4 * k4);
+        const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+        const float4* wp = reinterpret_cast<const float4*>(bs + (int64_t)k4 * 4 * N);
+        float w[4 * N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float4 t = wp[j];
+            w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4 * N; ++e) {
+            acc0[e % N] = fmaf(av0[e / N], w[e], acc0[e % N]);
+            acc1[e % N] = fmaf(av1[e / N], w[e], acc1[e % N]);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            acc0[n] += __shfl_xor_sync(0xffffffffu, acc0[n], o);
+            acc1[n] += __shfl_xor_sync(0xffffffffu, acc1[n], o);
+        }
+    }
+    if (ks == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            red[(warp * (kSN + 1) + n) * kSR + 2 * rp] = acc0[n];
+            red[(warp * (kSN + 1) + n) * kSR + 2 * rp + 1] = acc1[n];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < N * kSR; e += kST) {
+        const int n = e / kSR, rr = e % kSR;
+        float sum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kSW; ++wq) sum += red[(wq * (kSN + 1) + n) * kSR + rr];
+        out_t[n * kSR + rr] = sum;
+    }
+    __syncthreads();
+}
+// true if handled (N <= 16); the operand must already be complete in `bs` (caller has waited and synchronised)
+__device__ __forceinline__ bool phi_w_gemm_dispatch(int N, const float* A, int lda, int K, const float* bs, float* red, float* out_t) {
+    switch (N) {
+#define DGPRF_PW(n) case n: phi_w_gemm<n>(A, lda, K, bs, red, out_t); return true;
+        DGPRF_PW(1) DGPRF_PW(2) DGPRF_PW(3) DGPRF_PW(4) DGPRF_PW(5) DGPRF_PW(6) DGPRF_PW(7) DGPRF_PW(8)
+        DGPRF_PW(9) DGPRF_PW(10) DGPRF_PW(11) DGPRF_PW(12) DGPRF_PW(13) DGPRF_PW(14) DGPRF_PW(15) DGPRF_PW(16)
+#undef DGPRF_PW
+        default: return false;
+    }
 }
 
 __device__ __forceinline__ int padded_F(int F) { return ((F + 3) & ~3) + 4; }
@@ -210,7 +294,9 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
     float* red   = m_all + a.n_layers * a.dmax;          // [kSW][kSN+1][R]
     float* dphi  = red + kSW * (kSN + 1) * kSR;          // [R][Fmax_p]  dPhi, then dP in place (cos half)
     float* b_s   = dphi + kSR * a.Fmax;                  // [bs_cap] staging of W / z operands
-    float* phi_all = b_s + a.bs_cap;                     // per layer [R][F_p]
+    float* zr_s  = b_s + a.bs_cap;                       // [zr_cap] z rows of the backward T GEMM (prefetched), may be empty
+    float* phi_all = zr_s + a.zr_cap;                    // per layer [R][F_p]
+    float* zf_s  = dphi;                                 // forward only: the first zf_rows rows of z_l (dphi is idle then)
 
     const int tid = threadIdx.x;
     const int chain = blockIdx.y, grp = blockIdx.x;
@@ -231,6 +317,15 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
     }
     float* fcur = fa_t;      // F_{l-1} (transposed)
     float* fnext = fb_t;
+    // Operand prefetch (cp.async groups, oldest first): the leading rows of z_l sit in zf_s before layer l starts --
+    // z_0 is requested here, z_{l+1} right after GEMM #1 of layer l, so the L2 round trip hides under the Phi.W GEMM.
+    if (a.prefetch_w) {
+        const StepRowsLayer& y0 = a.layer[0];
+        const int nz0 = min(y0.d_prev + y0.d_x, (a.Fmax * kSR) / y0.M);
+        stage_async(zf_s, y0.z + chain * y0.z_cs, nz0 * y0.M);
+        cp_async_commit();
+    }
+    bool top_w_in_bs = false;                            // the last layer's W is still staged when the backward starts
     int tsi = 0;
 #define K9_STAMP() do { if (a.timing && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.timing[tsi] = clock64(); ++tsi; } while (0)
 #define K9_STAMP2() do { if (a.timing && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.timing[40 + l] = clock64(); } while (0)
@@ -250,12 +345,15 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         const float* Wl = y.W + chain * a.w_cs;
         const int F4 = (F + 3) & ~3;
         const bool w_fits = a.prefetch_w && (F4 + 4) * y.g <= a.bs_cap;  // whole W_l staged while GEMM #1 runs
+        const int nzp = a.prefetch_w ? min(d, (a.Fmax * kSR) / M) : 0;   // rows of z_l prefetched into zf_s
         if (w_fits) {
             stage_W_rows(b_s, Wl, 0, F, F4, y.g);
             cp_async_commit();
         }
         for (int e = tid; e < kSR * (Fp - F); e += kST)  // zero the K padding of Phi
             phi[(e / (Fp - F)) * Fp + F + e % (Fp - F)] = 0.f;
+        if (w_fits) cp_async_wait_but_newest();          // z_l has landed; W_l may still be in flight
+        else cp_async_wait_all();
         __syncthreads();
         K9_STAMP();
         for (int m = tid; m < M; m += kST) {
@@ -265,7 +363,8 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
             for (int q0 = 0; q0 < d; q0 += 20) {
                 float zr[20];
 #pragma unroll
-                for (int i = 0; i < 20; ++i) zr[i] = (q0 + i) < d ? __ldg(z + (int64_t)(q0 + i) * M + m) : 0.f;
+                for (int i = 0; i < 20; ++i)
+                    zr[i] = (q0 + i) < nzp ? zf_s[(q0 + i) * M + m] : ((q0 + i) < d ? __ldg(z + (int64_t)(q0 + i) * M + m) : 0.f);
 #pragma unroll
                 for (int i = 0; i < 20; ++i) {
                     const int q = q0 + i;
@@ -293,7 +392,22 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         }
         __syncthreads();
         K9_STAMP();
-        small_gemm_dispatch<true>(phi, Fp, Wl, 0, F, y.g, false, b_s, a.bs_cap, w_fits, red, fnext);
+        bool z_next = false;
+        if (a.prefetch_w && l + 1 < a.n_layers) {        // zf_s is free again: request the next layer's z rows
+            const StepRowsLayer& y2 = a.layer[l + 1];
+            const int nz2 = min(y2.d_prev + y2.d_x, (a.Fmax * kSR) / y2.M);
+            stage_async(zf_s, y2.z + chain * y2.z_cs, nz2 * y2.M);
+            cp_async_commit();
+            z_next = true;
+        }
+        bool done = false;
+        if (w_fits && y.g <= 16) {                       // whole W_l staged: register-blocked compile-time-N path
+            if (z_next) cp_async_wait_but_newest(); else cp_async_wait_all();
+            __syncthreads();
+            done = phi_w_gemm_dispatch(y.g, phi, Fp, F, b_s, red, fnext);
+        }
+        if (!done) small_gemm_dispatch<true>(phi, Fp, Wl, 0, F, y.g, false, b_s, a.bs_cap, w_fits, z_next && w_fits, red, fnext);
+        top_w_in_bs = w_fits;
         K9_STAMP();
         float* t = fcur; fcur = fnext; fnext = t;
     }
@@ -341,6 +455,7 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
     K9_STAMP();
 
     // =========================== backward ===========================
+    bool w_prefetched = false;
     for (int l = a.n_layers - 1; l >= 0; --l) {
         const StepRowsLayer& y = a.layer[l];
         const int M = y.M, g = y.g;
@@ -354,12 +469,25 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         //     coalesced stores (a thread-per-feature store pattern has a 4*g-byte stride between lanes).
         const int fc_max = min((F + 3) & ~3, ((a.bs_cap / g) - 4) & ~3);
         const int fb_max = min(kST, (kSW * (kSN + 1) * kSR) / g);      // features per store batch (tile = `red`)
+        // W_l may already be staged: the top layer's copy from the forward, or the prefetch issued during the T GEMM
+        // of the layer above.  The z rows of THIS layer's T GEMM are requested now and land during phase (a).
+        const bool top = l == a.n_layers - 1;
+        const bool w_ready = l > 0 && fc_max >= F && (top ? top_w_in_bs : w_prefetched);
+        bool z_ready = false;
+        if (a.prefetch_w && l > 0 && a.zr_cap > 0) {
+            z_ready = small_gemm_prefetch_z(y.z + chain * y.z_cs, M, M, y.d_prev, zr_s, a.zr_cap);
+            if (z_ready) cp_async_commit();
+        }
         for (int f0 = 0; f0 < F; f0 += fc_max) {
             const int fc = min(fc_max, F - f0);
             if (l > 0) {                                  // layer 0 needs no dPhi, hence no W
-                stage_W_rows(b_s, W, f0, fc, fc, g);
-                cp_async_commit();
-                cp_async_wait_all();
+                if (w_ready) {
+                    if (!top) { if (z_ready) cp_async_wait_but_newest(); else cp_async_wait_all(); }
+                } else {
+                    stage_W_rows(b_s, W, f0, fc, fc, g);
+                    cp_async_commit();
+                    cp_async_wait_all();
+                }
             }
             __syncthreads();
             for (int b0 = 0; b0 < fc; b0 += fb_max) {
@@ -413,7 +541,18 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         __syncthreads();
         K9_STAMP();
         // (c) T = dP z^T (first d_prev rows of z), R = rowsum(dP)
-        small_gemm_dispatch<false>(dphi, Fdp, y.z + chain * y.z_cs, M, M, y.d_prev, y.has_mean != 0, b_s, a.bs_cap, false, red, dFp);
+        w_prefetched = false;
+        if (a.prefetch_w && z_ready && l - 1 > 0) {      // b_s is idle during this T GEMM: request W_{l-1} for the next phase (a)
+            const StepRowsLayer& y1 = a.layer[l - 1];
+            const int F1 = y1.kind == DGPRF_KIND_RBF ? 2 * y1.M : y1.M;
+            if (min((F1 + 3) & ~3, ((a.bs_cap / y1.g) - 4) & ~3) >= F1) {
+                stage_W_rows(b_s, y1.W + chain * a.w_cs, 0, F1, F1, y1.g);
+                cp_async_commit();
+                w_prefetched = true;
+            }
+        }
+        small_gemm_dispatch<false>(dphi, Fdp, y.z + chain * y.z_cs, M, M, y.d_prev, y.has_mean != 0, z_ready ? zr_s : b_s,
+                                   z_ready ? a.zr_cap : a.bs_cap, z_ready, z_ready && w_prefetched, red, dFp);
         for (int e = tid; e < y.d_prev * kSR; e += kST) {
             const int q = e / kSR, r = e % kSR;
             float v = s_s[q] * dFp[e];
@@ -472,7 +611,25 @@ static int step_rows_bs_cap(const dgprf_model* m) {
     return (int)round_up(need, 4);
 }
 
-size_t dgprf_step_rows_smem(const dgprf_model* m) {
+// z rows of the widest backward T GEMM: d_prev x (M rounded to 4, + 4) floats (small_gemm's single-chunk layout)
+static int step_rows_zr_need(const dgprf_model* m) {
+    int64_t need = 0;
+    for (int l = 1; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        const int64_t n = (int64_t)y.d_prev * (((y.M + 3) & ~3) + 4);
+        if (n > need) need = n;
+    }
+    return (int)round_up(need, 4);
+}
+static size_t step_rows_smem_base(const dgprf_model* m);
+// the prefetch buffer is optional: it is dropped when it would push the CTA past the 227 KB limit
+static int step_rows_zr_cap(const dgprf_model* m) {
+    const int need = step_rows_zr_need(m);
+    return step_rows_smem_base(m) + sizeof(float) * (size_t)need <= 232448 ? need : 0;
+}
+size_t dgprf_step_rows_smem(const dgprf_model* m) { return step_rows_smem_base(m) + sizeof(float) * (size_t)step_rows_zr_cap(m); }
+
+static size_t step_rows_smem_base(const dgprf_model* m) {
     int64_t dmax = 1, Fmax = 1, phis = 0;
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
@@ -495,7 +652,7 @@ bool dgprf_step_rows_eligible(const dgprf_model* m, int B) {
     if ((int64_t)ceil_div(B, kSR) * m->n_chains > 160) return false;      // more than ~one wave: the layered kernels win
     for (int l = 0; l < m->n_layers; ++l)
         if (m->layer[l].g > kSN || m->layer[l].d_prev > kSN) return false;
-    return dgprf_step_rows_smem(m) <= 220 * 1024;
+    return step_rows_smem_base(m) <= 220 * 1024;
 }
 
 // upd != nullptr asks for the fused update; *fused tells the caller whether it was done (it needs a
@@ -527,7 +684,7 @@ int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, c
         if (y.d_prev + y.d_x > dmax) dmax = y.d_prev + y.d_x;
         if (F > Fmax) Fmax = F;
     }
-    a.dmax = (int32_t)round_up(dmax, 4); a.Fmax = (int32_t)Fmax; a.bs_cap = step_rows_bs_cap(m);
+    a.dmax = (int32_t)round_up(dmax, 4); a.Fmax = (int32_t)Fmax; a.bs_cap = step_rows_bs_cap(m); a.zr_cap = step_rows_zr_cap(m);
     const size_t smem = dgprf_step_rows_smem(m);
     static size_t configured = 0;
     if (smem > configured) {
