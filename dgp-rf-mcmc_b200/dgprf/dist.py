@@ -76,3 +76,29 @@ def combine_predictive(lse_local: torch.Tensor, n_samples_local: int, aux_sum_lo
         m = float(meta[1]) / (S * N)
         aux = math.sqrt(m) if aux_is_se else m
     return float(lp), aux
+
+
+def data_parallel_step(engine, X_local: torch.Tensor, Y_local: torch.Tensor, global_rows: int, data_size: float,
+                       lr: float, momentum_decay: float, temperature: float = 1.0, resample: bool = False,
+                       seed: int = 0, step: int = 0, group=None) -> torch.Tensor:
+    """One W-only sgmcmc_update (models/dgp.py:184-216) of a minibatch whose rows are split over the ranks.
+
+    Every rank runs forward / likelihood seed / backward on its rows (CUDA kernels, data term only), scales the
+    flat gradient by B_local / B_global, joins ONE all-reduce(sum) of [gW | sum_i ll_i], and applies the update
+    kernel to its replica with the same Philox (seed, step): the prior term theta/N is added inside the update,
+    once, after the reduction; replicas stay bit-identical without a broadcast.  Returns sum_i ll_i [C]."""
+    import ctypes as C
+    from . import _ffi
+    tot, gW, _ = engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False)
+    Cn, w_len = gW.shape
+    flat = torch.empty(Cn * w_len + Cn, device=gW.device, dtype=torch.float32)
+    torch.mul(gW.reshape(-1), dp_scale(X_local.shape[0], global_rows), out=flat[:Cn * w_len])
+    flat[Cn * w_len:] = tot
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    sw, nsw, _, _ = engine._segments()
+    _ffi.check(_ffi.lib().dgprf_sgmcmc_update(
+        engine.theta_w.data_ptr(), engine.mom_w.data_ptr(), w_len, w_len, Cn, flat.data_ptr(), w_len, 1, 0,
+        sw, nsw, float(lr), float(data_size), float(momentum_decay), float(temperature), int(bool(resample)),
+        int(seed), int(step), None, None, _ffi.stream_ptr()))
+    return flat[Cn * w_len:]
