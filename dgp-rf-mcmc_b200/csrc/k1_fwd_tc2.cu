@@ -112,14 +112,32 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
             sSq[tid] = tid < a.d ? expf(__ldg(ls + tid)) : 0.f;
             sMean[tid] = (mean != nullptr && tid < a.d) ? __ldg(mean + tid) : 0.f;
         }
-        for (int r = warp; r < V2_BM; r += V2_THREADS / 32) {
-            const int64_t row = row0 + r;
+        // 8 independent loads per thread in flight; the partial slabs of the previous layer are added slab by slab
+        // in slab order (the order of slab_load)
+        constexpr int PB = 8;
+        const float* fp = a.Fprev.ptr + chain * a.Fprev.cs;
+        for (int e0 = tid; e0 < V2_BM * 128; e0 += V2_THREADS * PB) {
+            float v[PB];
 #pragma unroll
-            for (int q = lane; q < 128; q += 32) {
-                float v = 0.f;
-                if (row < a.B && q < a.d)
-                    v = q < a.d_prev ? slab_load(a.Fprev, chain, row, q) : __ldg(X + row * a.ldx + (q - a.d_prev));
-                sIn[r * 129 + q] = v;
+            for (int u = 0; u < PB; ++u) {
+                const int e = e0 + u * V2_THREADS;
+                const int r = e >> 7, q = e & 127;
+                const int64_t row = row0 + r;
+                v[u] = (e < V2_BM * 128 && row < a.B && q >= a.d_prev && q < a.d) ? __ldg(X + row * a.ldx + (q - a.d_prev)) : 0.f;
+            }
+            for (int sl = 0; sl < a.Fprev.n_slabs; ++sl) {
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const int e = e0 + u * V2_THREADS;
+                    const int r = e >> 7, q = e & 127;
+                    const int64_t row = row0 + r;
+                    if (e < V2_BM * 128 && row < a.B && q < a.d_prev) v[u] += __ldg(fp + sl * a.Fprev.ss + row * a.Fprev.ld + q);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int e = e0 + u * V2_THREADS;
+                if (e < V2_BM * 128) sIn[(e >> 7) * 129 + (e & 127)] = v[u];
             }
         }
         __syncthreads();

@@ -18,7 +18,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 STEPS = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 PREC = os.environ.get("DGPRF_PRECISION", "tf32")
-B, D_in, M, L, N = 65536, 90, 4096, 5, 515345
+B, D_in, M, L, N = int(os.environ.get("DP_GLOBAL_BATCH", 65536)), 90, 4096, 5, 515345
 n_gp = [30, 30, 30, 30, 1]
 spec = ModelSpec.build(D_in, 1, [M] * L, n_gp, ["RBF"] * L, True, False, "gaussian")
 torch.manual_seed(0)                                  # identical initial replicas
@@ -50,6 +50,11 @@ if world > 1:
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     same = bool(lo.item() == hi.item())
+if rank == 0 and os.environ.get("DGPRF_BREAKDOWN"):
+    _ffi.profile_start()
+    D.data_parallel_step(e, Xl, Yl, step=999, **kw)
+    recs = _ffi.profile_stop()
+    print("kernel sum %.1f us:" % (1e3 * sum(t for _, t in recs)), " ".join(f"{nm}={t * 1e3:.0f}" for nm, t in recs))
 if rank == 0:
     print(json.dumps({"workload": "configs[4] data-parallel step", "n_gpus": world, "precision": PREC, "global_batch": B,
                       "rows_per_gpu": Xl.shape[0], "ms_per_step": ms.item(), "it_per_s": 1e3 / ms.item(), "scaling": "strong",
