@@ -141,7 +141,9 @@ __device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.as
 // approximations (abs error ~5e-7 on the reduced range).  Random-feature phases reach
 // |P| >> pi, where bare __sinf/__cosf lose all accuracy.
 __device__ __forceinline__ void sincos_cw(float x, float* s, float* c) {
-    const float k = rintf(x * 0.15915494309189535f);
+    // round(x / 2pi) by the 1.5 * 2^23 trick (two FADDs; rintf is an XU-pipe instruction like MUFU); exact for
+    // |x / 2pi| < 2^22, far beyond any phase the features can produce before sin/cos lose meaning in fp32
+    const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.f), -12582912.f);
     float r = fmaf(-k, 6.2831854820251465f, x);        // 2*pi rounded to fp32
     r = fmaf(-k, -1.7484555e-7f, r);                   // 2*pi - fp32(2*pi)
     *s = __sinf(r);

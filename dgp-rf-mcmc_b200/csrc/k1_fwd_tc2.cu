@@ -4,21 +4,25 @@
 //   * the A operand of GEMM #1, (in * exp(log_inv_ls)) split into tf32 hi + lo, is written ONCE per CTA into
 //     TENSOR MEMORY (tcgen05.st) and consumed from there by every column tile (tcgen05.mma with A in TMEM),
 //     so shared memory only holds the streamed operands;
-//   * roles:  warps 0-7  epilogue   tcgen05.ld P -> sincos/relu -> Phi tile (smem, UMMA/TMA swizzle)
-//             warp  8    MMA        one thread issues GEMM #1 (3xTF32) of tile t+1 and GEMM #2 of tile t
-//             warp  9    producer   one thread issues the TMA loads of the next z tile (tf32 hi/lo) and W tile
-//             warp  10   store      TMA store of the Phi tile (saved features)
+//   * roles:  warps 0-15 epilogue   tcgen05.ld P -> sincos/relu -> Phi tile (smem, UMMA/TMA swizzle)
+//             warp  16   MMA-1      one elected thread issues GEMM #1 (3xTF32 phases) of the tiles, running ahead
+//             warp  17   producer   one thread issues the TMA loads of the next z tile (tf32 hi/lo) and W tile
+//             warp  18   store      TMA store of the Phi tile (saved features)
+//             warp  19   MMA-2      one elected thread issues GEMM #2 (Phi.W) of each tile as soon as its Phi is in smem
+//     (two issuing threads: the tensor pipe runs about as fast as one thread can feed it, so with a single issuer
+//      the wait/poll code between the two GEMMs of a tile left it idle a third of the time)
 //     connected by mbarriers; P (D1) is double-buffered in TMEM and the z tile is a 2-stage ring (when it
 //     fits), so GEMM #1 of tile t+1 and the loads of tile t+2 run under the epilogue of tile t.
 //   * the streamed operands are pre-laid for TMA by a small prep kernel per launch: z^T split into tf32
 //     hi/lo, K-major, zero-padded to 128 K columns ([2][M][128]) and W^T rounded to tf32 ([NG][F]).
+#include <stdio.h>
 #include <stdlib.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
 constexpr int V2_BM = 128, V2_BN = 64;
-constexpr int V2_EPI_WARPS = 8;
-constexpr int V2_THREADS = (V2_EPI_WARPS + 3) * 32;                           // 352
+constexpr int V2_EPI_WARPS = 16;                 // 4 per TMEM lane quarter, 16 tile columns each
+constexpr int V2_THREADS = (V2_EPI_WARPS + 4) * 32;                           // 640
 constexpr int V2_HDR = 1024;                      // bias row + mbarriers + TMEM slot
 constexpr int V2_BLK = V2_BM * 128;               // [128 x 32 tf32] block
 constexpr int V2_BBLK = V2_BN * 128;              // [64 x 32 tf32] block
@@ -46,9 +50,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 }  // namespace tc
 
+// Straight-line MMA issue (one elected thread).  Every descriptor is base + compile-time offset and the accumulate
+// flags are constants, so the SASS is a run of UTCHMMA with independent 64-bit adds: with runtime k loops the
+// uniform-datapath loop / descriptor arithmetic costs ~65 cycles per k-step and bounds the whole kernel.
+// All NKB x 4 k-steps are issued: the A operand and the z tile are zero-padded beyond the input width.
+template <int NKB>
+__device__ __forceinline__ void issue_gemm1(uint32_t dcol, uint32_t tm_ahi, uint32_t tm_alo, uint64_t db, uint32_t idesc) {
+    constexpr uint32_t lo_off = (uint32_t)(NKB * V2_BBLK) >> 4;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t acol = 32 * kb + 8 * k4;
+            const uint64_t dbh = db + (uint32_t)((kb * V2_BBLK + k4 * 32) >> 4);
+            tc::umma_tf32_ts(dcol, tm_alo + acol, dbh, idesc, (kb | k4) != 0 ? 1u : 0u);
+            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbh + lo_off, idesc, 1u);
+            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbh, idesc, 1u);
+        }
+}
+template <int NB2, int NG>
+__device__ __forceinline__ void issue_gemm2(uint32_t tm_d2, uint64_t dphi, uint64_t dw, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+    for (int b = 0; b < NB2; ++b)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+            tc::umma_tf32(tm_d2, dphi + (uint32_t)((b * V2_BLK + k4 * 32) >> 4), dw + (uint32_t)((b * NG * 128 + k4 * 32) >> 4), idesc,
+                          (b | k4) != 0 ? 1u : acc_first);
+}
+
 template <int NG>
 __global__ void __launch_bounds__(V2_THREADS, 1)
-k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
+k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
            const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -70,13 +102,19 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chain = blockIdx.z, cs = blockIdx.y, row0 = blockIdx.x * V2_BM;
+    // debug timeline (DGPRF_TC2_TIMELINE=1): clock stamps of CTA 0, first 16 tiles, 12 events per tile
+#define TL(t, ev) do { if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) tl[(t) * 12 + (ev)] = clock64(); } while (0)
     const float* X = a.X + chain * a.x_cs;
     const float* ls = a.log_inv_ls + chain * a.h_cs;
     const float* mean = a.has_mean ? a.mean + chain * a.h_cs : nullptr;
     const bool rbf = a.kind == DGPRF_KIND_RBF;
     const float scale = (rbf ? 1.f : 1.41421356237f) * __expf(__ldg(a.log_amp + chain * a.h_cs)) * rsqrtf((float)a.M);
     const int n_ct = (a.M + V2_BN - 1) / V2_BN;
-    const int n_my = cs < n_ct ? (n_ct - cs + a.CS - 1) / a.CS : 0;        // column tiles of this CTA
+    // column split cs owns the CONTIGUOUS tiles [cs * per, cs * per + n_my): consecutive tiles of a CTA then store
+    // adjacent 256-byte pieces of the same Phi rows
+    const int per = (n_ct + a.CS - 1) / a.CS;
+    const int ct0 = cs * per;
+    const int n_my = ct0 < n_ct ? min(per, n_ct - ct0) : 0;
     const int n_kb = (a.d + 31) / 32;
     const int nb2 = rbf ? 4 : 2;
     const uint32_t b1_stage = 2u * n_kb * V2_BBLK;
@@ -142,30 +180,31 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
         }
         __syncthreads();
         if (warp < V2_EPI_WARPS) {
-            const int lq = warp & 3, kh = warp >> 2;
+            const int lq = warp & 3, kq = warp >> 2;              // TMEM lane quarter, 32-column K quarter
             const int r = 32 * lq + lane;
+            float* bpart = reinterpret_cast<float*>(sW) + 1024;  // [4][128] partial biases (sW is idle until the pipeline starts)
             float bsum = 0.f;
 #pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) {
+            for (int c16 = 0; c16 < 2; ++c16) {
                 float hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int q = 64 * kh + 16 * c16 + i;
+                    const int q = 32 * kq + 16 * c16 + i;
                     const float v = sIn[r * 129 + q];
                     bsum = fmaf(v, sMean[q], bsum);
                     const float x = v * sSq[q];
                     hi[i] = tc::to_tf32(x);
                     lo[i] = tc::to_tf32(x - hi[i]);
                 }
-                const uint32_t col = 64 * kh + 16 * c16;
+                const uint32_t col = 32 * kq + 16 * c16;
                 tc::tmem_st16(tm_ahi + ((uint32_t)(32 * lq) << 16) + col, hi);
                 tc::tmem_st16(tm_alo + ((uint32_t)(32 * lq) << 16) + col, lo);
             }
             tc::tmem_st_wait();
-            if (a.has_mean) {                     // bias_r = sum_q in[r][q] mean[q]: the two K halves of a row
-                if (kh == 0) bias_s[r] = bsum;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (kh == 1) bias_s[r] += bsum;
+            if (a.has_mean) {                     // bias_r = sum_q in[r][q] mean[q]: the four K quarters of a row, fixed order
+                bpart[kq * V2_BM + r] = bsum;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (kq == 0) bias_s[r] = ((bpart[r] + bpart[V2_BM + r]) + bpart[2 * V2_BM + r]) + bpart[3 * V2_BM + r];
             }
         }
     }
@@ -178,24 +217,27 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
 
     if (warp < V2_EPI_WARPS) {
         // ===================================== EPILOGUE =====================================
-        const int lq = warp & 3, chh = warp >> 2;
+        const int lq = warp & 3, cq = warp >> 2;               // TMEM lane quarter, 16-column quarter of the tile
         const int r = 32 * lq + lane;
         const float bias = a.has_mean ? bias_s[r] : 0.f;
+        const int pb = cq >> 1, pc = (cq & 1) * 4;             // 32-column Phi block and first 16-byte chunk inside it
         for (int t = 0; t < n_my; ++t) {
-            const int c0 = (cs + t * a.CS) * V2_BN;
+            const int c0 = (ct0 + t) * V2_BN;
             const int buf = t & 1;
             tc::mbar_wait(d1_full + buf, (t >> 1) & 1);
+            if (tid == 0) TL(t, 0);
             tc::tc_fence_after();
-            float p[32];
-            tc::tmem_ld32(tm_d1 + 64 * buf + ((uint32_t)(32 * lq) << 16) + 32 * chh, p);
+            float p[16];
+            tc::tmem_ld16(tm_d1 + 64 * buf + ((uint32_t)(32 * lq) << 16) + 16 * cq, p);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(d1_empty + buf);          // P is in registers: the buffer is free
-            float f1[32];
+            if (tid == 0) TL(t, 1);
+            float f1[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const bool live = (c0 + 32 * chh + i) < a.M;
+            for (int i = 0; i < 16; ++i) {
+                const bool live = (c0 + 16 * cq + i) < a.M;
                 const float x = p[i] + bias;
                 if (rbf) {
                     float s, c;
@@ -206,18 +248,21 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
                     p[i] = live ? scale * fmaxf(x, 0.f) : 0.f;
                 }
             }
+            if (tid == 0) TL(t, 2);
             tc::mbar_wait(phi_empty, (t & 1) ^ 1);                   // GEMM #2 and the store of tile t-1 are done
+            if (tid == 0) TL(t, 3);
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                *reinterpret_cast<float4*>(sPhi + chh * V2_BLK + tc::sw128_chunk(r, c4)) =
+            for (int c4 = 0; c4 < 4; ++c4) {
+                *reinterpret_cast<float4*>(sPhi + pb * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
                     make_float4(p[4 * c4], p[4 * c4 + 1], p[4 * c4 + 2], p[4 * c4 + 3]);
                 if (rbf)
-                    *reinterpret_cast<float4*>(sPhi + (2 + chh) * V2_BLK + tc::sw128_chunk(r, c4)) =
+                    *reinterpret_cast<float4*>(sPhi + (2 + pb) * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
                         make_float4(f1[4 * c4], f1[4 * c4 + 1], f1[4 * c4 + 2], f1[4 * c4 + 3]);
             }
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(phi_full);
+            if (tid == 0) TL(t, 4);
         }
         // ---- final: F partial slab of this column split ----
         if (a.do_gemm2 && n_my > 0 && warp < 4) {
@@ -242,67 +287,62 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
         // The whole warp walks the loop converged (waits included); one elected lane issues.  Descriptors are
         // built once: advancing along K or to another block only adds to the 14-bit start-address field.
         const uint64_t dB1 = tc::make_desc_sw128(tc::smem_u32(sB1));
+        for (int t = 0; t < n_my; ++t) {
+            const int buf = t & 1;
+            const int s1 = t % NS1;
+            tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
+            tc::mbar_wait(b1_full + s1, (t / NS1) & 1);
+            if (lane == 0) TL(t, 5);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint64_t db = dB1 + ((s1 * b1_stage) >> 4);
+                const uint32_t dcol = tm_d1 + 64 * buf;
+                switch (n_kb) {
+                    case 1: issue_gemm1<1>(dcol, tm_ahi, tm_alo, db, IDESC1); break;
+                    case 2: issue_gemm1<2>(dcol, tm_ahi, tm_alo, db, IDESC1); break;
+                    case 3: issue_gemm1<3>(dcol, tm_ahi, tm_alo, db, IDESC1); break;
+                    default: issue_gemm1<4>(dcol, tm_ahi, tm_alo, db, IDESC1); break;
+                }
+                TL(t, 11);
+                tc::umma_commit(b1_empty + s1);        // z tile consumed
+                tc::umma_commit(d1_full + buf);        // P ready
+            }
+            __syncwarp();
+            if (lane == 0) TL(t, 6);
+        }
+    } else if (warp == V2_EPI_WARPS + 3) {
+        // ===================================== MMA-2 ISSUER =====================================
         const uint64_t dPhi = tc::make_desc_sw128(tc::smem_u32(sPhi));
         const uint64_t dW = tc::make_desc_sw128(tc::smem_u32(sW));
-        const uint32_t lo_off = (uint32_t)(n_kb * V2_BBLK) >> 4;
-        // software pipeline: GEMM #1 of tile t is issued before GEMM #2 of tile t-1
-        for (int t = 0; t <= n_my; ++t) {
-            if (t < n_my) {
-                const int buf = t & 1;
-                const int s1 = t % NS1;
-                tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
-                tc::mbar_wait(b1_full + s1, (t / NS1) & 1);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint64_t db = dB1 + ((s1 * b1_stage) >> 4);
-                    const uint32_t dcol = tm_d1 + 64 * buf;
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        const int kleft = a.d - 32 * kb;
-                        const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
-                        for (int k4 = 0; k4 < ksteps; ++k4) {
-                            const uint32_t acol = 32 * kb + 8 * k4;
-                            const uint64_t dbh = db + (uint32_t)((kb * V2_BBLK + k4 * 32) >> 4);
-                            const uint64_t dbl = dbh + lo_off;
-                            tc::umma_tf32_ts(dcol, tm_alo + acol, dbh, IDESC1, (kb | k4) != 0);
-                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbl, IDESC1, 1u);
-                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dbh, IDESC1, 1u);
-                        }
-                    }
-                    tc::umma_commit(b1_empty + s1);        // z tile consumed
-                    tc::umma_commit(d1_full + buf);        // P ready
+        for (int u = 0; u < n_my; ++u) {
+            const int ws = u & 1;
+            tc::mbar_wait(phi_full, u & 1);
+            if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u >> 1) & 1);
+            if (lane == 0) TL(u, 7);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                if (a.do_gemm2) {
+                    const uint64_t dw = dW + (uint32_t)((ws * 4 * NG * 128) >> 4);
+                    if (rbf) issue_gemm2<4, NG>(tm_d2, dPhi, dw, IDESC2, u != 0 ? 1u : 0u);
+                    else issue_gemm2<2, NG>(tm_d2, dPhi, dw, IDESC2, u != 0 ? 1u : 0u);
+                    tc::umma_commit(w_empty + ws);
                 }
-                __syncwarp();
+                tc::umma_commit(phi_empty);            // Phi tile consumed by the tensor core (1 of 2 arrivals)
+                if (u == n_my - 1) tc::umma_commit(d2_full);
             }
-            if (t > 0) {
-                const int u = t - 1, ws = u & 1;
-                tc::mbar_wait(phi_full, u & 1);
-                if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u >> 1) & 1);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    if (a.do_gemm2) {
-                        const uint64_t dw = dW + (uint32_t)((ws * 4 * NG * 128) >> 4);
-                        for (int b = 0; b < nb2; ++b)
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)
-                                tc::umma_tf32(tm_d2, dPhi + (uint32_t)((b * V2_BLK + k4 * 32) >> 4),
-                                              dw + (uint32_t)((b * NG * 128 + k4 * 32) >> 4), IDESC2, (u | b | k4) != 0);
-                        tc::umma_commit(w_empty + ws);
-                    }
-                    tc::umma_commit(phi_empty);            // Phi tile consumed by the tensor core (1 of 2 arrivals)
-                    if (u == n_my - 1) tc::umma_commit(d2_full);
-                }
-                __syncwarp();
-            }
+            __syncwarp();
+            if (lane == 0) TL(u, 8);
         }
     } else if (warp == V2_EPI_WARPS + 1) {
         // ===================================== TMA PRODUCER =====================================
         if (tc::elect_one()) {
             const int zc = a.zt_cs != 0 ? chain : 0;
             for (int t = 0; t < n_my; ++t) {
-                const int c0 = (cs + t * a.CS) * V2_BN;
+                const int c0 = (ct0 + t) * V2_BN;
                 // ---- z tile (B of GEMM #1): rows = feature columns, K-major, tf32 hi blocks then lo blocks ----
                 const int s1 = t % NS1;
                 tc::mbar_wait(b1_empty + s1, ((t / NS1) & 1) ^ 1);
+                TL(t, 9);
                 tc::mbar_expect_tx(b1_full + s1, b1_stage);
                 const uint32_t b1 = tc::smem_u32(sB1) + s1 * b1_stage;
                 for (int kb = 0; kb < n_kb; ++kb) {
@@ -313,6 +353,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
                 if (a.do_gemm2) {
                     const int ws = t & 1;
                     tc::mbar_wait(w_empty + ws, ((t >> 1) & 1) ^ 1);
+                    TL(t, 10);
                     tc::mbar_expect_tx(w_full + ws, (uint32_t)nb2 * NG * 128);
                     for (int b = 0; b < nb2; ++b)
                         tc::tma_load_3d(&map_wt, tc::smem_u32(sW + (ws * 4 + b) * (NG * 128)), w_full + ws,
@@ -324,7 +365,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const __grid_constant__ CUtensorMap m
         // ===================================== STORE WARP =====================================
         if (tc::elect_one()) {
             for (int t = 0; t < n_my; ++t) {
-                const int c0 = (cs + t * a.CS) * V2_BN;
+                const int c0 = (ct0 + t) * V2_BN;
                 tc::mbar_wait(phi_full, t & 1);
                 if (a.Phi != nullptr) {
                     for (int b = 0; b < 2; ++b) {
@@ -424,8 +465,24 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     FwdArgs b = a;
     b.zt_cs = a.z_cs != 0 ? 1 : 0;
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG><<<grid, V2_THREADS, smem, st>>>(b, ns1, mc, ms, mz, mw); }
+    static long long* tl = nullptr;                       // debug timeline (DGPRF_TC2_TIMELINE=1)
+    static int tl_calls = 0;
+    if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
+    if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG><<<grid, V2_THREADS, smem, st>>>(b, ns1, tl, mc, ms, mz, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
+    if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
+        long long h[16 * 12];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, tl, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[9];                         // producer's first stamp
+        fprintf(stderr, "tc2 timeline (cycles since the producer started; train=%d)\n tile | epi: P-ready P-loaded sincos-done phi-free stored | mma: g1-go g1-issued g2-go g2-issued | prod: z-slot w-slot | g1-mmas-issued(before commits)\n", a.Phi != nullptr);
+        for (int t = 0; t < 16; ++t) {
+            fprintf(stderr, " %3d |", t);
+            for (int e = 0; e < 12; ++e) fprintf(stderr, " %7lld%s", h[t * 12 + e] ? h[t * 12 + e] - t0 : -1LL, (e == 4 || e == 8 || e == 10) ? " |" : "");
+            fprintf(stderr, "\n");
+        }
+    }
     return DGPRF_OK;
 }
 
