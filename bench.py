@@ -338,21 +338,40 @@ def run_ours(args, rank, world):
         tF = 2 * tM
         phi_bytes = 4.0 * tB * tF
 
-        def tc_entry(name, alg_flops, exe_flops, what):
+        # write-only HBM ceiling (a 1 GiB fill): HBM3e writes are slower than reads, and the forward's saved-feature
+        # store is a pure write stream, so that is the roofline it is held against
+        wbuf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            wbuf.fill_(1)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        w0.record(stream)
+        for _ in range(5):
+            wbuf.fill_(2)
+        w1.record(stream)
+        torch.cuda.synchronize()
+        hbm_write_gbs = 5.0 * (1 << 30) / (w0.elapsed_time(w1) * 1e-3) / 1e9
+        del wbuf
+
+        def tc_entry(name, alg_flops, exe_flops, what, hbm_peak, hbm_peak_name):
             if name not in tper:
                 return None
             us = 1e3 * statistics.mean(tper[name])
             return {"kernel": name, "what": what, "avg_us": us,
                     "algorithmic_tflops": alg_flops / us / 1e6, "executed_tensor_tflops": exe_flops / us / 1e6,
                     "tensor_frac_executed": exe_flops / us / 1e6 / tf32_peak,
-                    "saved_feature_gbs": phi_bytes / us / 1e3, "hbm_frac": phi_bytes / us / 1e3 / pk["hbm_gbs"]}
+                    "saved_feature_gbs": phi_bytes / us / 1e3, "hbm_frac": phi_bytes / us / 1e3 / hbm_peak,
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_kind": hbm_peak_name}
         tc_layer = {
             "workload": f"one [RF->GP] layer at configs[4] scale: B={tB}, d={td}, M={tM}, n_gp={tg}, RBF, tf32 mode",
-            "tf32_peak_tflops": tf32_peak, "hbm_peak_gbs": pk["hbm_gbs"], "peak_source": pk_src,
-            "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * td * tM + tF * tg),
-                            "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored (TMA)"),
+            "tf32_peak_tflops": tf32_peak, "hbm_copy_peak_gbs": pk["hbm_gbs"], "hbm_write_only_gbs": hbm_write_gbs,
+            "peak_source": pk_src + " (copy, bf16); write-only measured live with a 1 GiB fill",
+            "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * 128 * tM + tF * tg),
+                            "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored (TMA): bound by the write stream",
+                            hbm_write_gbs, "write-only"),
             "bwd": tc_entry("k2_bwd_tc2", 4.0 * tB * tF * tg, 4.0 * tB * tF * 32,
-                            "dPhi = dF.W^T, gW += Phi^T.dF (accumulators resident in TMEM); Phi loaded (TMA ring)"),
+                            "dPhi = dF.W^T, gW += Phi^T.dF (accumulators resident in TMEM); Phi loaded (TMA ring)",
+                            pk["hbm_gbs"], "copy"),
         }
         del te, tX, tY
         torch.cuda.empty_cache()
