@@ -43,7 +43,7 @@ constexpr int kTN = 64;        // random-feature columns per tile
 constexpr int kKC = 32;        // K chunk of GEMM #1 (input width)
 constexpr int kMaxCS = 8;      // column splits of the SIMT kernels -> partial slabs of F / dF_prev
 constexpr int kMaxSlabs = 16;  // most slabs any producer writes (tensor-core forward with 32-wide tiles)
-constexpr int kMaxRS = 16;     // row splits     -> partial slabs of gW
+constexpr int kMaxRS = 18;     // row splits     -> partial slabs of gW
 constexpr int kThreads = 256;
 
 static inline int col_splits(int M) { int t = ceil_div(M, kTN); return t < kMaxCS ? t : kMaxCS; }

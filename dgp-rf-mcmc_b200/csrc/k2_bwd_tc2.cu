@@ -18,12 +18,28 @@
 #include "tc_common.cuh"
 
 constexpr int B2_BM = 128, B2_BN = 64, B2_NG = 32;
-constexpr int B2_THREADS = 256;
+constexpr int B2_EPI_WARPS = 8;
+constexpr int B2_THREADS = (B2_EPI_WARPS + 1) * 32;     // 8 epilogue warps + the issuer warp
 constexpr int B2_BLK = B2_BM * 128;            // bytes of a [128 x 32 tf32] block
 constexpr int B2_HDR = 2048;                   // R_s | s_s | m_s | mbarriers | TMEM slot
 constexpr int B2_MAX_LOC = 10;                 // resident gW tiles: 10 x 32 TMEM columns
 constexpr uint32_t B2_TMEM_COLS = 512;         // D1 128 | D3 64 | D2 320
 
+namespace tc {
+__device__ __forceinline__ void mbar_arrive_b2(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tc
+
+// Roles: warps 0-7 = epilogue (dF staging, dP, dF_prev, gW write-out); warp 8 = issuer: one elected thread issues
+// every TMA load and every UMMA, so no epilogue warp ever stalls behind MMA issue.  The two sides talk through
+// mbarriers only:
+//   issuer -> epilogue   barA  MMA-1(k) done (dPhi in D1)        barB  MMA-3(k) done (dP / z tiles free, T final at a
+//                        row end)                                 barC  MMA-2(k) done (Phi stage and dF tile consumed)
+//   epilogue -> issuer   e_read  every warp has copied its Phi rows of tile k to registers (stage may be refilled)
+//                        d1_free every warp holds its dPhi values of tile k in registers (MMA-1(k+1) may overwrite D1)
+//                        dp_full every warp has written dP(k)
+//                        df_full the dF tile of the next row tile is staged
 __global__ void __launch_bounds__(B2_THREADS, 1)
 k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
            const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_z) {
@@ -36,10 +52,15 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     uint64_t* phi_full = bars + 0;    // [2] TMA complete_tx
     uint64_t* w_full = bars + 2;      // TMA complete_tx
     uint64_t* z_full = bars + 3;      // TMA complete_tx
-    uint64_t* barA = bars + 4;        // MMA-1 of a tile complete (dPhi ready)
-    uint64_t* barB = bars + 5;        // MMA-3 of a tile complete
-    uint64_t* barC = bars + 6;        // MMA-2 of a tile complete (Phi stage and dF tile consumed)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* barA = bars + 4;
+    uint64_t* barB = bars + 5;
+    uint64_t* barC = bars + 6;
+    uint64_t* e_read = bars + 7;      // count 8 (stage 0; stage 1 is bars + 11)
+    uint64_t* dp_full = bars + 8;     // count 8
+    uint64_t* df_full = bars + 9;     // count 8
+    uint64_t* d1_free = bars + 10;    // count 8
+    uint64_t* e_read1 = bars + 11;    // count 8
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     uint8_t* sPhi = sm + B2_HDR;                     // 2 stages x 4 blocks: cos 0,1 | sin 2,3   (32-byte-atom swizzle)
     uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
     uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
@@ -59,9 +80,10 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const int n_rloc = rs < n_rt ? (n_rt - rs + a.RS - 1) / a.RS : 0;         // row tiles of this CTA
     const int T = n_loc * n_rloc;
 
-    if (warp == 0) tc::tmem_alloc(tmem_slot, B2_TMEM_COLS);
+    if (warp == B2_EPI_WARPS) tc::tmem_alloc(tmem_slot, B2_TMEM_COLS);
     if (tid == 0) {
         for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
+        for (int i = 7; i < 12; ++i) tc::mbar_init(bars + i, B2_EPI_WARPS);
         tc::mbar_fence_init();
     }
     if (tid < 64) {
@@ -80,125 +102,160 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_d1 = tmem_base, tm_d3 = tmem_base + 128, tm_d2 = tmem_base + 192;
 
-    constexpr uint32_t IDESC1 = tc::make_idesc_tf32(B2_BM, 2 * B2_BN);
-    constexpr uint32_t IDESC2 = tc::make_idesc_tf32_mn(B2_BM, B2_NG);
-    const uint32_t IDESC3 = tc::make_idesc_tf32(B2_BM, NQ > 0 ? NQ : 16);
-    const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
-
-    // tile k of this CTA = (row tile k / n_loc, column tile k % n_loc); the loaders run on one elected thread
-    auto load_phi = [&](int k) {
-        const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
-        tc::mbar_expect_tx(phi_full + s, phi_bytes);
-        for (int b = 0; b < 2; ++b) {
-            tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
-            if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
-        }
-    };
-    auto load_w = [&](int k) {
-        const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
-        tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
-        tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
-        if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
-    };
-    auto load_z = [&](int k) {
-        const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
-        tc::mbar_expect_tx(z_full, 2u * NQ * 128);
-        for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 0, zc);
-    };
-    if (warp == 0 && T > 0 && tc::elect_one()) {
-        load_phi(0);
-        if (T > 1) load_phi(1);
-        load_w(0);
-        if (NQ > 0) load_z(0);
-    }
-
-    const uint64_t d_dF = tc::make_desc_sw128(tc::smem_u32(sdF));
-    const uint64_t d_W = tc::make_desc_sw128(tc::smem_u32(sW));
-    const uint64_t d_dP = tc::make_desc_sw128(tc::smem_u32(sdP));
-    const uint64_t d_Z = tc::make_desc_sw128(tc::smem_u32(sZ));
-    const uint64_t d_dF2 = tc::make_desc_mn_b32(tc::smem_u32(sdF2), B2_BLK, 512);
-    const uint64_t d_Phi = tc::make_desc_mn_b32(tc::smem_u32(sPhi), B2_BLK, 512);
-    const int k1steps = (a.g + 7) / 8;
-
-    const int lq = warp & 3, hh = warp >> 2;             // TMEM lane quarter, 32-column half of the tile
-    const int r = 32 * lq + lane;
-    float rsum = 0.f;
-
-    // dF tile of a row tile (A of MMA-1, B of MMA-2): the partial slabs are summed in slab order (the order of
-    // slab_load), one slab per pass so that a thread keeps 16 independent loads in flight
-    auto stage_dF = [&](int row0) {
-        constexpr int NE = B2_BM * 32 / B2_THREADS;
-        float v[NE];
-        const float* base = a.dF.ptr + chain * a.dF.cs;
+    if (warp == B2_EPI_WARPS) {
+        // ============================================ ISSUER ============================================
+        if (T > 0 && tc::elect_one()) {
+            constexpr uint32_t IDESC1 = tc::make_idesc_tf32(B2_BM, 2 * B2_BN);
+            constexpr uint32_t IDESC2 = tc::make_idesc_tf32_mn(B2_BM, B2_NG);
+            const uint32_t IDESC3 = tc::make_idesc_tf32(B2_BM, NQ > 0 ? NQ : 16);
+            const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
+            const uint64_t d_dF = tc::make_desc_sw128(tc::smem_u32(sdF));
+            const uint64_t d_W = tc::make_desc_sw128(tc::smem_u32(sW));
+            const uint64_t d_dP = tc::make_desc_sw128(tc::smem_u32(sdP));
+            const uint64_t d_Z = tc::make_desc_sw128(tc::smem_u32(sZ));
+            const uint64_t d_dF2 = tc::make_desc_mn_b32(tc::smem_u32(sdF2), B2_BLK, 512);
+            const uint64_t d_Phi = tc::make_desc_mn_b32(tc::smem_u32(sPhi), B2_BLK, 512);
+            const int k1steps = (a.g + 7) / 8;
+            // tile k of this CTA = (row tile k / n_loc, column tile k % n_loc)
+            auto load_phi = [&](int k) {
+                const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
+                tc::mbar_expect_tx(phi_full + s, phi_bytes);
+                for (int b = 0; b < 2; ++b) {
+                    tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+                    if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+                }
+            };
+            auto load_w = [&](int k) {
+                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+                tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
+                tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
+                if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
+            };
+            auto load_z = [&](int k) {
+                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+                tc::mbar_expect_tx(z_full, 2u * NQ * 128);
+                for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 0, zc);
+            };
+            // MMA-1: dPhi = dF W_tile^T -> D1 (straight-line issue; the unused k-steps are predicated off)
+            auto mma1 = [&](int k) {
+                tc::mbar_wait(w_full, k & 1);
+                tc::tc_fence_after();
+                tc::umma_tf32(tm_d1, d_dF, d_W, IDESC1, 0u);
+                if (k1steps > 1) tc::umma_tf32(tm_d1, d_dF + 2, d_W + 2, IDESC1, 1u);
+                if (k1steps > 2) tc::umma_tf32(tm_d1, d_dF + 4, d_W + 4, IDESC1, 1u);
+                if (k1steps > 3) tc::umma_tf32(tm_d1, d_dF + 6, d_W + 6, IDESC1, 1u);
+                tc::umma_commit(barA);
+            };
+            // MMA-2: gW tile il += Phi_tile^T dF (K = the 128 batch rows, 8 per instruction), accumulated over row tiles
+            auto mma2 = [&](int k) {
+                const int s = k & 1, il = k % n_loc, rl = k / n_loc;
+                tc::mbar_wait(phi_full + s, (k >> 1) & 1);
+                tc::tc_fence_after();
+                const uint64_t dphi = d_Phi + (uint32_t)((s * 4 * B2_BLK) >> 4);
+                const uint32_t dcol = tm_d2 + il * B2_NG;
 #pragma unroll
-        for (int u = 0; u < NE; ++u) v[u] = 0.f;
-        for (int sl = 0; sl < a.dF.n_slabs; ++sl) {
-            const float* p = base + sl * a.dF.ss;
+                for (int k8 = 0; k8 < B2_BM / 8; ++k8)
+                    tc::umma_tf32(dcol, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, k8 != 0 ? 1u : (rl != 0 ? 1u : 0u));
+                tc::umma_commit(barC);
+            };
+
+            load_phi(0);
+            if (T > 1) load_phi(1);
+            load_w(0);
+            if (NQ > 0) load_z(0);
+            tc::mbar_wait(df_full, 0);
+            mma1(0);
+            int rows_done = 0;                                      // df_full phases consumed so far - 1
+            for (int k = 0; k < T; ++k) {
+                const int il = k % n_loc;
+                const bool row_end = il == n_loc - 1;
+                mma2(k);
+                tc::mbar_wait(barA, k & 1);                         // MMA-1(k) done: the W tile is free
+                if (k + 1 < T) load_w(k + 1);
+                if (NQ > 0 && k > 0) {                              // MMA-3(k-1) done: the z tile is free
+                    tc::mbar_wait(barB, (k - 1) & 1);
+                    load_z(k);
+                }
+                if (k + 2 < T) {                                    // refill stage k & 1 once MMA-2(k) and the epilogue's reads are done
+                    tc::mbar_wait((k & 1) ? e_read1 : e_read, (k >> 1) & 1);
+                    tc::mbar_wait(barC, k & 1);
+                    load_phi(k + 2);
+                }
+                // inside a row tile, MMA-1 of the next tile goes out as soon as the epilogue holds dPhi(k) in registers,
+                // i.e. under the epilogue's math / stores; at a row end it has to wait for the next dF tile
+                tc::mbar_wait(d1_free, k & 1);
+                tc::tc_fence_after();
+                if (!row_end && k + 1 < T) mma1(k + 1);
+                tc::mbar_wait(dp_full, k & 1);                      // dP(k) written
+                tc::tc_fence_after();
+                if (NQ > 0) {
+                    tc::mbar_wait(z_full, k & 1);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::umma_tf32(tm_d3, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
+                                          d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3, (b | k4) != 0 ? 1u : (il != 0 ? 1u : 0u));
+                }
+                tc::umma_commit(barB);
+                if (row_end && k + 1 < T) {                         // the next row tile's dF must be staged first
+                    ++rows_done;
+                    tc::mbar_wait(df_full, rows_done & 1);
+                    tc::tc_fence_after();
+                    mma1(k + 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================================ EPILOGUE ============================================
+        const int lq = warp & 3, hh = warp >> 2;             // TMEM lane quarter, 32-column half of the tile
+        const int r = 32 * lq + lane;
+        float rsum = 0.f;
+        constexpr int ET = B2_EPI_WARPS * 32;
+        // dF tile of a row tile (A of MMA-1, B of MMA-2): the partial slabs are summed in slab order (the order of
+        // slab_load), one slab per pass so that a thread keeps 16 independent loads in flight
+        auto stage_dF = [&](int row0) {
+            constexpr int NE = B2_BM * 32 / ET;
+            float v[NE];
+            const float* base = a.dF.ptr + chain * a.dF.cs;
+#pragma unroll
+            for (int u = 0; u < NE; ++u) v[u] = 0.f;
+            for (int sl = 0; sl < a.dF.n_slabs; ++sl) {
+                const float* p = base + sl * a.dF.ss;
+#pragma unroll
+                for (int u = 0; u < NE; ++u) {
+                    const int e = tid + u * ET;
+                    const int rr = e >> 5, j = e & 31;
+                    const int64_t row = row0 + rr;
+                    const float x = (row < a.B && j < a.g) ? __ldg(p + row * a.dF.ld + j) : 0.f;
+                    v[u] = sl == 0 ? x : v[u] + x;
+                }
+            }
 #pragma unroll
             for (int u = 0; u < NE; ++u) {
-                const int e = tid + u * B2_THREADS;
+                const int e = tid + u * ET;
                 const int rr = e >> 5, j = e & 31;
-                const int64_t row = row0 + rr;
-                const float x = (row < a.B && j < a.g) ? __ldg(p + row * a.dF.ld + j) : 0.f;
-                v[u] = sl == 0 ? x : v[u] + x;
+                const float t = tc::to_tf32(v[u]);
+                *reinterpret_cast<float*>(sdF + tc::sw128_off(rr, j)) = t;
+                *reinterpret_cast<float*>(sdF2 + tc::sw128b32_off(rr, j)) = t;
             }
-        }
-#pragma unroll
-        for (int u = 0; u < NE; ++u) {
-            const int e = tid + u * B2_THREADS;
-            const int rr = e >> 5, j = e & 31;
-            const float t = tc::to_tf32(v[u]);
-            *reinterpret_cast<float*>(sdF + tc::sw128_off(rr, j)) = t;
-            *reinterpret_cast<float*>(sdF2 + tc::sw128b32_off(rr, j)) = t;
-        }
-        tc::fence_async_smem();
-    };
-    // MMA-1 (dPhi -> D1; barA) then MMA-2 (gW tile il += Phi^T dF, accumulated over the row tiles; barC) of tile k.
-    // Runs on the elected thread.  Only MMA-1 is on the critical path of the dP epilogue.
-    auto issue_mma12 = [&](int k) {
-        const int s = k & 1, il = k % n_loc, rl = k / n_loc;
-        tc::mbar_wait(w_full, k & 1);
-        tc::tc_fence_after();
-        for (int k4 = 0; k4 < k1steps; ++k4)
-            tc::umma_tf32(tm_d1, d_dF + 2 * k4, d_W + 2 * k4, IDESC1, k4 != 0);
-        tc::umma_commit(barA);
-        tc::mbar_wait(phi_full + s, (k >> 1) & 1);
-        tc::tc_fence_after();
-        const uint64_t dphi = d_Phi + (uint32_t)((s * 4 * B2_BLK) >> 4);
-#pragma unroll 4
-        for (int k8 = 0; k8 < B2_BM / 8; ++k8)
-            tc::umma_tf32(tm_d2 + il * B2_NG, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, (rl | k8) != 0);
-        tc::umma_commit(barC);
-    };
-
-    if (T > 0) {
-        stage_dF(rs * B2_BM);
-        __syncthreads();
-        if (warp == 0) {
-            if (tc::elect_one()) issue_mma12(0);
+            tc::fence_async_smem();
             __syncwarp();
-        }
-    }
+            if (lane == 0) tc::mbar_arrive_b2(df_full);
+        };
+        if (T > 0) stage_dF(rs * B2_BM);
 
-    for (int k = 0; k < T; ++k) {
-        const int il = k % n_loc, rl = k / n_loc;
-        const int row0 = (rs + rl * a.RS) * B2_BM;
-        const int s = k & 1;
-        const bool row_end = il == n_loc - 1;
-        tc::mbar_wait(barA, k & 1);                       // dPhi of tile k is in D1
-        tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is read by every thread below
-        tc::tc_fence_after();
-        if (warp == 0) {
-            // the tensor pipe is in order: MMA-1(k) done => W tile free; MMA-3(k-1) done => z tile and dP tile free
-            if (tc::elect_one()) {
-                if (k + 1 < T) load_w(k + 1);
-                if (NQ > 0 && k > 0) load_z(k);
-            }
-            __syncwarp();
-        }
-        // ---- epilogue 1: dP from dPhi (TMEM) and the Phi tile (smem) -> dP tile (A of MMA-3), row sums.
-        //      The thread's Phi values go to registers first so the ring stage can be refilled right away. ----
-        {
+        for (int k = 0; k < T; ++k) {
+            const int il = k % n_loc, rl = k / n_loc;
+            const int row0 = (rs + rl * a.RS) * B2_BM;
+            const int s = k & 1;
+            const bool row_end = il == n_loc - 1;
+            tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is read by every thread below
+            // ---- the thread's Phi values go to registers first so the ring stage can be refilled right away.  One
+            //      release barrier per stage: its next phase needs the stage's next TMA load, which the issuer only
+            //      requests after consuming this phase, so it can never run two phases ahead of the issuer's wait ----
             const uint8_t* ph = sPhi + s * 4 * B2_BLK;
             float4 pcv[8], psv[8];
 #pragma unroll
@@ -206,136 +263,118 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 pcv[cc] = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc));
                 if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc));
             }
-            __syncthreads();
-            if (warp == 0) {          // every thread has read stage s; once MMA-2(k) is done too, prefetch tile k+2
-                if (k + 2 < T && tc::elect_one()) {
-                    tc::mbar_wait(barC, k & 1);
-                    load_phi(k + 2);
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float dc[16], ds[16];
-                const uint32_t lane_addr = (uint32_t)(32 * lq) << 16;
-                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh + 16 * pass, dc);
-                if (rbf) tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh + 16 * pass, ds);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int cc = 4 * pass + c4;                // 16-byte chunk inside the 32-wide block
-                    const float4 pc = pcv[cc];
-                    float4 o;
-                    if (rbf) {
-                        const float4 ps = psv[cc];
-                        o.x = pc.x * ds[4 * c4 + 0] - ps.x * dc[4 * c4 + 0];
-                        o.y = pc.y * ds[4 * c4 + 1] - ps.y * dc[4 * c4 + 1];
-                        o.z = pc.z * ds[4 * c4 + 2] - ps.z * dc[4 * c4 + 2];
-                        o.w = pc.w * ds[4 * c4 + 3] - ps.w * dc[4 * c4 + 3];
-                    } else {
-                        o.x = pc.x > 0.f ? dc[4 * c4 + 0] * arc_scale : 0.f;
-                        o.y = pc.y > 0.f ? dc[4 * c4 + 1] * arc_scale : 0.f;
-                        o.z = pc.z > 0.f ? dc[4 * c4 + 2] * arc_scale : 0.f;
-                        o.w = pc.w > 0.f ? dc[4 * c4 + 3] * arc_scale : 0.f;
-                    }
-                    rsum += (o.x + o.y) + (o.z + o.w);
-                    o.x = tc::to_tf32(o.x); o.y = tc::to_tf32(o.y); o.z = tc::to_tf32(o.z); o.w = tc::to_tf32(o.w);
-                    *reinterpret_cast<float4*>(sdP + hh * B2_BLK + tc::sw128_chunk(r, cc)) = o;
-                }
-            }
-        }
-        if (row_end) R_s[hh * B2_BM + r] = rsum;
-        tc::tc_fence_before();
-        tc::fence_async_smem();
-        __syncthreads();
-        // ---- MMA-3 (T += dP z^T); inside a row tile MMA-1/2 of the next tile follow at once ----
-        if (warp == 0) {
-            if (tc::elect_one()) {
-                tc::tc_fence_after();
-                if (NQ > 0) {
-                    tc::mbar_wait(z_full, k & 1);
-                    tc::tc_fence_after();
-                    for (int b = 0; b < 2; ++b)
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            tc::umma_tf32(tm_d3, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
-                                          d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3, (il | b | k4) != 0);
-                }
-                tc::umma_commit(barB);
-                if (!row_end && k + 1 < T) issue_mma12(k + 1);
-            }
             __syncwarp();
-        }
-        if (row_end) {
-            // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
-            tc::mbar_wait(barB, k & 1);
+            if (lane == 0) tc::mbar_arrive_b2(s ? e_read1 : e_read);
+            tc::mbar_wait(barA, k & 1);                       // dPhi of tile k is in D1
             tc::tc_fence_after();
-            if (NQ > 0 && warp < 4 && a.Dpart != nullptr) {
-                const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
-                const float Rr = R_s[r] + R_s[B2_BM + r];
-                for (int qc = 0; qc < NQ / 16; ++qc) {
-                    float t[16];
-                    tc::tmem_ld16(tm_d3 + ((uint32_t)(32 * warp) << 16) + 16 * qc, t);
-                    tc::tmem_ld_wait();
-                    if (row < a.B) {
-                        float* dst = a.Dpart + chain * a.d_cs + ((int64_t)cs * a.B + row) * a.d_prev;
+            // ---- dPhi of the thread's row x 32 columns -> registers, then D1 is free for MMA-1 of the next tile ----
+            float dcv[32], dsv[32];
+            {
+                const uint32_t lane_addr = (uint32_t)(32 * lq) << 16;
+                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh, dcv);
+                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh + 16, dcv + 16);
+                if (rbf) {
+                    tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh, dsv);
+                    tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh + 16, dsv + 16);
+                }
+                tc::tmem_ld_wait();
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_b2(d1_free);
+            if (k > 0) tc::mbar_wait(barB, (k - 1) & 1);      // MMA-3(k-1) done: the dP tile may be overwritten
+            // ---- dP -> dP tile (A of MMA-3), row sums ----
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int q = 16 * qc + i;
-                            if (q < a.d_prev) {
-                                float v = s_s[q] * t[i];
-                                if (a.has_mean) v = fmaf(m_s[q], Rr, v);
-                                dst[q] = v;
+            for (int cc = 0; cc < 8; ++cc) {                  // 16-byte chunk inside the 32-wide block
+                const float4 pc = pcv[cc];
+                const float* dc = dcv + 4 * cc;
+                float4 o;
+                if (rbf) {
+                    const float4 ps = psv[cc];
+                    const float* ds = dsv + 4 * cc;
+                    o.x = pc.x * ds[0] - ps.x * dc[0];
+                    o.y = pc.y * ds[1] - ps.y * dc[1];
+                    o.z = pc.z * ds[2] - ps.z * dc[2];
+                    o.w = pc.w * ds[3] - ps.w * dc[3];
+                } else {
+                    o.x = pc.x > 0.f ? dc[0] * arc_scale : 0.f;
+                    o.y = pc.y > 0.f ? dc[1] * arc_scale : 0.f;
+                    o.z = pc.z > 0.f ? dc[2] * arc_scale : 0.f;
+                    o.w = pc.w > 0.f ? dc[3] * arc_scale : 0.f;
+                }
+                rsum += (o.x + o.y) + (o.z + o.w);
+                o.x = tc::to_tf32(o.x); o.y = tc::to_tf32(o.y); o.z = tc::to_tf32(o.z); o.w = tc::to_tf32(o.w);
+                *reinterpret_cast<float4*>(sdP + hh * B2_BLK + tc::sw128_chunk(r, cc)) = o;
+            }
+            tc::tc_fence_before();
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_b2(dp_full);
+            if (row_end) {
+                // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
+                R_s[hh * B2_BM + r] = rsum;
+                rsum = 0.f;
+                tc::mbar_wait(barB, k & 1);                    // T = sum over the row tile's column tiles is final
+                tc::tc_fence_after();
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s complete
+                if (NQ > 0 && warp < 4 && a.Dpart != nullptr) {
+                    const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
+                    const float Rr = R_s[r] + R_s[B2_BM + r];
+                    for (int qc = 0; qc < NQ / 16; ++qc) {
+                        float t[16];
+                        tc::tmem_ld16(tm_d3 + ((uint32_t)(32 * warp) << 16) + 16 * qc, t);
+                        tc::tmem_ld_wait();
+                        if (row < a.B) {
+                            float* dst = a.Dpart + chain * a.d_cs + ((int64_t)cs * a.B + row) * a.d_prev;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int q = 16 * qc + i;
+                                if (q < a.d_prev) {
+                                    float v = s_s[q] * t[i];
+                                    if (a.has_mean) v = fmaf(m_s[q], Rr, v);
+                                    dst[q] = v;
+                                }
                             }
                         }
                     }
                 }
-            }
-            rsum = 0.f;
-            if (k + 1 < T) {
-                // next row tile: its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
-                tc::mbar_wait(barC, k & 1);
-                stage_dF((rs + (rl + 1) * a.RS) * B2_BM);
                 tc::tc_fence_before();
-                __syncthreads();
-                if (warp == 0) {
-                    if (tc::elect_one()) { tc::tc_fence_after(); issue_mma12(k + 1); }
-                    __syncwarp();
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s and D3 are read: the next row tile may reuse them
+                if (k + 1 < T) {
+                    // its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
+                    tc::mbar_wait(barC, k & 1);
+                    stage_dF((rs + (rl + 1) * a.RS) * B2_BM);
                 }
             }
         }
-    }
-    if (T > 0) tc::mbar_wait(barC, (T - 1) & 1);           // the last MMA-2: every gW tile is final
-    tc::tc_fence_after();
-
-    // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    if (warp < 4) {
-        const int fl = 32 * warp + lane;                               // feature row inside [cos 64 | sin 64]
-        for (int i = 0; i < n_loc; ++i) {
-            const int c0 = (cs + i * a.CS) * B2_BN;
-            const int col = c0 + (fl & (B2_BN - 1));
-            const bool live = col < a.M && (rbf || fl < B2_BN);
-            const int64_t frow = (fl >= B2_BN ? a.M : 0) + col;
-            float* dst = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss + frow * a.g;
+        if (T > 0) tc::mbar_wait(barC, (T - 1) & 1);           // the last MMA-2: every gW tile is final
+        tc::tc_fence_after();
+        // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
+        if (warp < 4) {
+            const int fl = 32 * warp + lane;                               // feature row inside [cos 64 | sin 64]
+            for (int i = 0; i < n_loc; ++i) {
+                const int c0 = (cs + i * a.CS) * B2_BN;
+                const int col = c0 + (fl & (B2_BN - 1));
+                const bool live = col < a.M && (rbf || fl < B2_BN);
+                const int64_t frow = (fl >= B2_BN ? a.M : 0) + col;
+                float* dst = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss + frow * a.g;
 #pragma unroll
-            for (int c16 = 0; c16 < B2_NG / 16; ++c16) {
-                float v[16];
-                tc::tmem_ld16(tm_d2 + i * B2_NG + ((uint32_t)(32 * warp) << 16) + 16 * c16, v);
-                tc::tmem_ld_wait();
-                if (live) {
+                for (int c16 = 0; c16 < B2_NG / 16; ++c16) {
+                    float v[16];
+                    tc::tmem_ld16(tm_d2 + i * B2_NG + ((uint32_t)(32 * warp) << 16) + 16 * c16, v);
+                    tc::tmem_ld_wait();
+                    if (live) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (16 * c16 + j < a.g) dst[16 * c16 + j] = T > 0 ? v[j] : 0.f;
+                        for (int j = 0; j < 16; ++j)
+                            if (16 * c16 + j < a.g) dst[16 * c16 + j] = T > 0 ? v[j] : 0.f;
+                    }
                 }
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, B2_TMEM_COLS);
+    if (warp == B2_EPI_WARPS) tc::tmem_dealloc(tmem_base, B2_TMEM_COLS);
 }
 
 // W [F, g] -> wp [F][32]: zero-padded, tf32-rounded rows (a TMA row stride must be a multiple of 16 bytes)
