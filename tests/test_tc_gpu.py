@@ -32,6 +32,11 @@ CASES = {
     # grids large enough for the pipelined (warp-specialised, A-in-TMEM) forward kernel k1_fwd_tc2
     "pipelined_rbf_mean": (RegressionDGP, 9, 1, 3, 512, [9, 9, 1], None, True, True, 2048),
     "pipelined_arc_wide": (ClassificationDGP, 100, 10, 2, [512, 320], [28, 10], ["ARC", "RBF"], True, False, 2100),
+    # three K blocks of the TMEM-resident A operand (input widths 70 / 110), n_gp = 40 -> 64-column GEMM #2 template,
+    # v1 backward for the wide layer and pipelined backward (d_prev = 40) for the next; ragged last row / column tiles
+    "pipelined_kb3_g40": (RegressionDGP, 70, 3, 2, [708, 516], [40, 3], None, True, True, 1990),
+    # two K blocks, arc-cosine through the pipelined backward (zero-filled sin halves), many row tiles per CTA
+    "pipelined_arc_kb2": (ClassificationDGP, 50, 5, 3, 512, [12, 20, 5], ["ARC", "ARC", "RBF"], True, False, 4500),
 }
 
 
@@ -134,3 +139,17 @@ def test_tc_sampling_step():
     for n in names:
         assert rel_err(e.view(n), new[n]) < TF32_TOL, n
         assert rel_err(e.view(n, "mom"), m_new[n]) < TF32_TOL, n
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("pipelined")])
+def test_pipelined_cases_run_the_pipelined_kernels(name):
+    """No silent fallback: the library's event hook must list the warp-specialised kernels for these shapes."""
+    model, X, Y = build(name)
+    model.set_precision("tf32")
+    model.grad_U(X, Y, 5000)
+    _ffi.profile_start()
+    model.grad_U(X, Y, 5000)
+    names = [nm for nm, _ in _ffi.profile_stop()]
+    assert "k1_fwd_tc2" in names, names
+    assert "k2_bwd_tc2" in names, names
+    assert "k1_fwd_simt" not in names and "k2_bwd_simt" not in names, names
