@@ -80,8 +80,8 @@ struct WsLayout {
     int RS;        // row splits of the layered backward (gW slabs)
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
-    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, total;
-    int64_t n_dfsum;
+    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, total;
+    int64_t n_dfsum, n_hpart;
 };
 
 static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
@@ -146,7 +146,7 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
             s.n_rpart = (int64_t)s.CS * B;              s.rpart = take(s.n_rpart);
         }
         if (mode >= DGPRF_MODE_TRAIN && m->precision == DGPRF_PREC_TF32 &&
-            dgprf_bwd_tc2_shape_ok(B, y.M, y.g, y.d_prev, s.CS, w->RS)) {
+            dgprf_bwd_tc2_shape_ok(y.M, y.g, layer_d(y), y.d_prev, s.CS, mode == DGPRF_MODE_HYPER)) {
             s.bwd2 = 1;
             s.n_wp = dgprf_bwd_tc2_wp_floats(layer_F(y));
             s.wp = take(s.n_wp);
@@ -180,7 +180,13 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         w->gridbar = off;                               // two 32-bit words {count, generation}, zero-initialised
         off += 256;
     }
-    if (mode == DGPRF_MODE_HYPER) w->ghyp = take(w->h_len);
+    if (mode == DGPRF_MODE_HYPER) {
+        w->ghyp = take(w->h_len);
+        int dmax = 1;
+        for (int l = 0; l < m->n_layers; ++l) if (layer_d(m->layer[l]) > dmax) dmax = layer_d(m->layer[l]);
+        w->n_hpart = (int64_t)dgprf_hyper_row_blocks(B) * (2 * dmax + 1);      // row-block partials of the hyper reduction
+        w->hpart = take(w->n_hpart);
+    }
     for (int l = 0; l + 1 < m->n_layers; ++l)          // pre-summed dF of a pipelined TC backward (one slab instead of CS)
         if (w->L[l].bwd2 && (int64_t)B * m->layer[l].g > w->n_dfsum) w->n_dfsum = (int64_t)B * m->layer[l].g;
     if (w->n_dfsum > 0) w->dfsum = take(w->n_dfsum);
@@ -362,6 +368,7 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
             h.Fcur = fpart_of(m, w, ws, l, B);
             h.log_inv_ls = a.log_inv_ls; h.h_cs = m->h_cs;
             h.gH = wsf(ws, w.ghyp); h.gh_cs = w.h_len;
+            h.part = wsf(ws, w.hpart); h.part_cs = w.n_hpart;
             h.off_log_amp = y.off_log_amp; h.off_log_inv_ls = y.off_log_inv_ls; h.off_mean = y.off_mean;
             rc = dgprf_launch_hyper_reduce(h, m->n_chains, st);
             if (rc) return rc;

@@ -12,7 +12,9 @@
 //     flight during tile t and t+1;
 //   * the W rows and z rows of a column tile are TMA loads too (W from a zero-padded copy [F][32] made by a prep
 //     kernel because a TMA row stride must be a multiple of 16 bytes; z directly from the model's spectral draws).
-// W-only mode, n_gp <= 32, d_prev <= 64; other shapes stay on k2_bwd_tc.cu / the SIMT kernel.
+// n_gp <= 32.  W-only mode: d_prev <= 64.  Hyper mode (stochastic-EM / full-Bayes gradients): T is formed for ALL input
+// columns (width <= 128, two passes of 64 z rows through the same z tile), and the raw T and R = rowsum(dP) are written as
+// the partial slabs k_hyper_reduce consumes.  Other shapes stay on k2_bwd_tc.cu / the SIMT kernel.
 #include <stdlib.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -60,7 +62,8 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     uint64_t* df_full = bars + 9;     // count 8
     uint64_t* d1_free = bars + 10;    // count 8
     uint64_t* e_read1 = bars + 11;    // count 8
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* barZ = bars + 12;       // first z pass of MMA-3 done (hyper mode with more than 64 input columns)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     uint8_t* sPhi = sm + B2_HDR;                     // 2 stages x 4 blocks: cos 0,1 | sin 2,3   (32-byte-atom swizzle)
     uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
     uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
@@ -72,7 +75,10 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const int chain = blockIdx.z, cs = blockIdx.y, rs = blockIdx.x;
     const bool rbf = a.kind == DGPRF_KIND_RBF;
     const float arc_scale = 1.41421356237f * __expf(__ldg(a.log_amp + chain * a.h_cs)) * rsqrtf((float)a.M);
-    const int NQ = a.d_prev > 0 ? ((a.d_prev + 15) & ~15) : 0;      // UMMA N of MMA-3
+    const bool hyper = a.hyper != 0;
+    // input columns T is formed for: all of them in hyper mode, the previous layer's outputs otherwise
+    const int NQ = hyper ? ((a.d + 15) & ~15) : (a.d_prev > 0 ? ((a.d_prev + 15) & ~15) : 0);
+    const int nq0 = NQ < 64 ? NQ : 64, nq1 = NQ - nq0;               // UMMA N of the (up to two) MMA-3 passes
     const int zc = a.z_cs != 0 ? chain : 0;
 
     const int n_ct = (a.M + B2_BN - 1) / B2_BN, n_rt = (a.B + B2_BM - 1) / B2_BM;
@@ -84,6 +90,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     if (tid == 0) {
         for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
         for (int i = 7; i < 12; ++i) tc::mbar_init(bars + i, B2_EPI_WARPS);
+        tc::mbar_init(barZ, 1);
         tc::mbar_fence_init();
     }
     if (tid < 64) {
@@ -100,14 +107,15 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_d1 = tmem_base, tm_d3 = tmem_base + 128, tm_d2 = tmem_base + 192;
+    const uint32_t tm_d1 = tmem_base, tm_d3 = tmem_base + 128, tm_d2 = tmem_base + (hyper ? 256 : 192);
 
     if (warp == B2_EPI_WARPS) {
         // ============================================ ISSUER ============================================
         if (T > 0 && tc::elect_one()) {
             constexpr uint32_t IDESC1 = tc::make_idesc_tf32(B2_BM, 2 * B2_BN);
             constexpr uint32_t IDESC2 = tc::make_idesc_tf32_mn(B2_BM, B2_NG);
-            const uint32_t IDESC3 = tc::make_idesc_tf32(B2_BM, NQ > 0 ? NQ : 16);
+            const uint32_t IDESC3a = tc::make_idesc_tf32(B2_BM, nq0 > 0 ? nq0 : 16);
+            const uint32_t IDESC3b = tc::make_idesc_tf32(B2_BM, nq1 > 0 ? nq1 : 16);
             const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
             const uint64_t d_dF = tc::make_desc_sw128(tc::smem_u32(sdF));
             const uint64_t d_W = tc::make_desc_sw128(tc::smem_u32(sW));
@@ -131,11 +139,12 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
                 if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
             };
-            auto load_z = [&](int k) {
+            auto load_z = [&](int k, int pass) {                    // z rows [64 pass, 64 pass + nq0) of the column tile
                 const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
-                tc::mbar_expect_tx(z_full, 2u * NQ * 128);
-                for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 0, zc);
+                tc::mbar_expect_tx(z_full, 2u * nq0 * 128);
+                for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 64 * pass, zc);
             };
+            int zph = 0;                                            // z_full phases consumed
             // MMA-1: dPhi = dF W_tile^T -> D1 (straight-line issue; the unused k-steps are predicated off)
             auto mma1 = [&](int k) {
                 tc::mbar_wait(w_full, k & 1);
@@ -162,7 +171,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             load_phi(0);
             if (T > 1) load_phi(1);
             load_w(0);
-            if (NQ > 0) load_z(0);
+            if (NQ > 0) load_z(0, 0);
             tc::mbar_wait(df_full, 0);
             mma1(0);
             int rows_done = 0;                                      // df_full phases consumed so far - 1
@@ -174,7 +183,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 if (k + 1 < T) load_w(k + 1);
                 if (NQ > 0 && k > 0) {                              // MMA-3(k-1) done: the z tile is free
                     tc::mbar_wait(barB, (k - 1) & 1);
-                    load_z(k);
+                    load_z(k, 0);
                 }
                 if (k + 2 < T) {                                    // refill stage k & 1 once MMA-2(k) and the epilogue's reads are done
                     tc::mbar_wait((k & 1) ? e_read1 : e_read, (k >> 1) & 1);
@@ -189,14 +198,27 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 tc::mbar_wait(dp_full, k & 1);                      // dP(k) written
                 tc::tc_fence_after();
                 if (NQ > 0) {
-                    tc::mbar_wait(z_full, k & 1);
+                    tc::mbar_wait(z_full, zph++ & 1);
                     tc::tc_fence_after();
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
                             tc::umma_tf32(tm_d3, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
-                                          d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3, (b | k4) != 0 ? 1u : (il != 0 ? 1u : 0u));
+                                          d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3a, (b | k4) != 0 ? 1u : (il != 0 ? 1u : 0u));
+                    if (nq1 > 0) {                                  // second pass: z rows 64.. through the same tile
+                        tc::umma_commit(barZ);
+                        tc::mbar_wait(barZ, k & 1);
+                        load_z(k, 1);
+                        tc::mbar_wait(z_full, zph++ & 1);
+                        tc::tc_fence_after();
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                tc::umma_tf32(tm_d3 + 64, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
+                                              d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3b, (b | k4) != 0 ? 1u : (il != 0 ? 1u : 0u));
+                    }
                 }
                 tc::umma_commit(barB);
                 if (row_end && k + 1 < T) {                         // the next row tile's dF must be staged first
@@ -317,23 +339,26 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 tc::mbar_wait(barB, k & 1);                    // T = sum over the row tile's column tiles is final
                 tc::tc_fence_after();
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s complete
-                if (NQ > 0 && warp < 4 && a.Dpart != nullptr) {
+                if (warp < 4) {
                     const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
                     const float Rr = R_s[r] + R_s[B2_BM + r];
+                    if (hyper && row < a.B) a.Rpart[chain * a.r_cs + (int64_t)cs * a.B + row] = Rr;
                     for (int qc = 0; qc < NQ / 16; ++qc) {
                         float t[16];
                         tc::tmem_ld16(tm_d3 + ((uint32_t)(32 * warp) << 16) + 16 * qc, t);
                         tc::tmem_ld_wait();
                         if (row < a.B) {
-                            float* dst = a.Dpart + chain * a.d_cs + ((int64_t)cs * a.B + row) * a.d_prev;
+                            float* dst = a.Dpart != nullptr ? a.Dpart + chain * a.d_cs + ((int64_t)cs * a.B + row) * a.d_prev : nullptr;
+                            float* tdst = hyper ? a.Tpart + chain * a.t_cs + ((int64_t)cs * a.B + row) * a.d : nullptr;
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 const int q = 16 * qc + i;
-                                if (q < a.d_prev) {
+                                if (dst != nullptr && q < a.d_prev) {
                                     float v = s_s[q] * t[i];
                                     if (a.has_mean) v = fmaf(m_s[q], Rr, v);
                                     dst[q] = v;
                                 }
+                                if (tdst != nullptr && q < a.d) tdst[q] = t[i];     // raw T for the hyper-gradient reduction
                             }
                         }
                     }
@@ -391,18 +416,19 @@ k_prep_bwd_tc2(const float* __restrict__ W, int64_t w_cs, int F, int g, float* _
 static constexpr size_t kB2Smem = 1024 + B2_HDR + 8 * (size_t)B2_BLK + 2 * (size_t)B2_BLK + 2 * (size_t)B2_BLK +
                                   (size_t)B2_BLK + 2 * 64 * 128;
 
-bool dgprf_bwd_tc2_shape_ok(int B, int M, int g, int d_prev, int CS, int RS) {
+bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper) {
     // a row split beyond the last row tile is fine (its CTA writes a zero gW slab); every column split must own a
-    // tile because it owns a dF_prev slab
+    // tile because it owns a dF_prev slab.  Hyper mode keeps T for all d <= 128 input columns in TMEM (128 columns),
+    // which leaves room for 8 resident gW tiles instead of 10.
     const int n_ct = ceil_div(M, B2_BN);
-    (void)B; (void)RS;
-    return (M % 4) == 0 && g <= B2_NG && d_prev <= 64 && CS <= n_ct && ceil_div(n_ct, CS) <= B2_MAX_LOC &&
+    const int max_loc = hyper ? 8 : B2_MAX_LOC;
+    return (M % 4) == 0 && g <= B2_NG && d_prev <= 64 && (!hyper || d <= 128) && CS <= n_ct && ceil_div(n_ct, CS) <= max_loc &&
            getenv("DGPRF_NO_TC2") == nullptr;
 }
 int64_t dgprf_bwd_tc2_wp_floats(int F) { return (int64_t)F * B2_NG; }
 
 bool dgprf_bwd_tc2_supported(const BwdArgs& a) {
-    return !a.hyper && a.wp != nullptr && (a.phi_cs % 4) == 0 && dgprf_bwd_tc2_shape_ok(a.B, a.M, a.g, a.d_prev, a.CS, a.RS);
+    return a.wp != nullptr && (a.phi_cs % 4) == 0 && dgprf_bwd_tc2_shape_ok(a.M, a.g, a.d, a.d_prev, a.CS, a.hyper);
 }
 
 int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
@@ -428,9 +454,9 @@ int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
     }
     rc = dgprf_make_tmap_3d(&mw, a.wp, B2_NG, a.F, n_chains, B2_NG, (uint64_t)a.F * B2_NG, B2_BN);
     if (rc) return rc;
-    if (a.d_prev > 0) {
-        const int NQ = (a.d_prev + 15) & ~15;
-        rc = dgprf_make_tmap_3d(&mz, a.z, a.M, a.d, a.z_cs != 0 ? n_chains : 1, a.M, a.z_cs, NQ);
+    const int NQ = a.hyper ? ((a.d + 15) & ~15) : (a.d_prev > 0 ? ((a.d_prev + 15) & ~15) : 0);
+    if (NQ > 0) {
+        rc = dgprf_make_tmap_3d(&mz, a.z, a.M, a.d, a.z_cs != 0 ? n_chains : 1, a.M, a.z_cs, NQ < 64 ? NQ : 64);
         if (rc) return rc;
     }
     dim3 grid(a.RS, a.CS, n_chains);

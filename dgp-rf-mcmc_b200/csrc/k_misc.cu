@@ -64,53 +64,86 @@ int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_
 //   d log_inv_ls[q] = exp(log_inv_ls[q]) * sum_i in[i,q] * T[i,q]
 //   d mean[q]       = sum_i in[i,q] * R[i]
 //   d log_amp       = sum_ij dF[i,j] * F[i,j]
-// grid (ceil(d/32)+1, C): the last block of each chain does log_amp.
-__global__ void __launch_bounds__(256) k_hyper_reduce(const HypArgs a) {
+// Two launches so that large minibatches use the whole GPU and the result stays deterministic: row block rb of
+// `rows_per` rows writes part[rb] = [ls partial (d) | mean partial (d) | log_amp partial], then one CTA per chain adds the
+// row blocks in order.  The partial slabs (T, R, F, dF) are summed slab by slab in slab order.
+__device__ __forceinline__ float slab_sum_rt(const SlabMat& m, int chain, int64_t row, int col) {
+    const float* p = m.ptr + chain * m.cs + row * m.ld + col;
+    float v = __ldg(p);
+    for (int s = 1; s < m.n_slabs; ++s) v += __ldg(p + s * m.ss);
+    return v;
+}
+__global__ void __launch_bounds__(256) k_hyper_partial(const HypArgs a) {
     __shared__ float red_a[8][33];
     __shared__ float red_b[8][33];
     __shared__ float red[32];
-    const int chain = blockIdx.y;
-    const int nqb = (a.d + 31) / 32;
-    float* gH = a.gH + chain * a.gh_cs;
-    if ((int)blockIdx.x == nqb) {
-        float acc = 0.f;
-        const int64_t n = (int64_t)a.B * a.g;
-        for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
-            const int64_t row = e / a.g; const int j = (int)(e % a.g);
-            acc += slab_load(a.dF, chain, row, j) * slab_load(a.Fcur, chain, row, j);
-        }
-        acc = block_sum(acc, red);
-        if (threadIdx.x == 0) gH[a.off_log_amp] = acc;
-        return;
-    }
+    const int chain = blockIdx.y, rb = blockIdx.x;
+    const int64_t r0 = (int64_t)rb * a.rows_per, r1 = min((int64_t)a.B, r0 + a.rows_per);
+    float* part = a.part + chain * a.part_cs + (int64_t)rb * (2 * a.d + 1);
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int q = blockIdx.x * 32 + lane;
-    float acc_ls = 0.f, acc_mu = 0.f;
-    if (q < a.d) {
-        const float* X = a.X + chain * a.x_cs;
-        for (int64_t row = rg; row < a.B; row += 8) {
-            const float in = q < a.d_prev ? slab_load(a.Fprev, chain, row, q)
-                                          : __ldg(X + row * a.ldx + (q - a.d_prev));
-            acc_ls = fmaf(in, slab_load(a.T, chain, row, q), acc_ls);
-            if (a.has_mean) acc_mu = fmaf(in, slab_load(a.R, chain, row, 0), acc_mu);
+    const float* X = a.X + chain * a.x_cs;
+    for (int q0 = 0; q0 < a.d; q0 += 32) {
+        const int q = q0 + lane;
+        float acc_ls = 0.f, acc_mu = 0.f;
+        if (q < a.d) {
+#pragma unroll 4
+            for (int64_t row = r0 + rg; row < r1; row += 8) {
+                const float in = q < a.d_prev ? slab_sum_rt(a.Fprev, chain, row, q) : __ldg(X + row * a.ldx + (q - a.d_prev));
+                acc_ls = fmaf(in, slab_sum_rt(a.T, chain, row, q), acc_ls);
+                if (a.has_mean) acc_mu = fmaf(in, slab_sum_rt(a.R, chain, row, 0), acc_mu);
+            }
         }
-    }
-    red_a[rg][lane] = acc_ls;
-    red_b[rg][lane] = acc_mu;
-    __syncthreads();
-    if (rg == 0 && q < a.d) {
-        float s = 0.f, m = 0.f;
+        red_a[rg][lane] = acc_ls;
+        red_b[rg][lane] = acc_mu;
+        __syncthreads();
+        if (rg == 0 && q < a.d) {
+            float s = 0.f, m = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { s += red_a[r][lane]; m += red_b[r][lane]; }
-        const float sq = expf(__ldg(a.log_inv_ls + chain * a.h_cs + q));
-        gH[a.off_log_inv_ls + q] = sq * s;
-        if (a.has_mean) gH[a.off_mean + q] = m;
+            for (int r = 0; r < 8; ++r) { s += red_a[r][lane]; m += red_b[r][lane]; }
+            part[q] = s;
+            part[a.d + q] = m;
+        }
+        __syncthreads();
+    }
+    float acc = 0.f;
+    const int64_t n = (r1 - r0) * a.g;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const int64_t row = r0 + e / a.g; const int j = (int)(e % a.g);
+        acc += slab_sum_rt(a.dF, chain, row, j) * slab_sum_rt(a.Fcur, chain, row, j);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) part[2 * a.d] = acc;
+}
+__global__ void __launch_bounds__(256) k_hyper_final(const HypArgs a) {
+    const int chain = blockIdx.x;
+    const float* part = a.part + chain * a.part_cs;
+    float* gH = a.gH + chain * a.gh_cs;
+    const int w = 2 * a.d + 1;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) {
+        float s = 0.f;
+        for (int rb = 0; rb < a.n_rb; ++rb) s += part[(int64_t)rb * w + i];
+        if (i < a.d) gH[a.off_log_inv_ls + i] = expf(__ldg(a.log_inv_ls + chain * a.h_cs + i)) * s;
+        else if (i < 2 * a.d) { if (a.has_mean) gH[a.off_mean + (i - a.d)] = s; }
+        else gH[a.off_log_amp] = s;
     }
 }
 
-int dgprf_launch_hyper_reduce(const HypArgs& a, int n_chains, cudaStream_t st) {
-    dim3 grid((a.d + 31) / 32 + 1, n_chains);
-    { ProfScope _ps("k8_hyper_reduce", st); k_hyper_reduce<<<grid, 256, 0, st>>>(a); }
+// row blocks of the hyper reduction for a minibatch of B rows: <= 2 per SM, >= 128 rows each
+int dgprf_hyper_row_blocks(int B) {
+    int n = ceil_div(B, 128);
+    return n < 1 ? 1 : (n > 296 ? 296 : n);
+}
+
+int dgprf_launch_hyper_reduce(const HypArgs& a0, int n_chains, cudaStream_t st) {
+    HypArgs a = a0;
+    a.n_rb = dgprf_hyper_row_blocks(a.B);
+    a.rows_per = ceil_div(a.B, a.n_rb);
+    a.n_rb = ceil_div(a.B, a.rows_per);
+    {
+        ProfScope _ps("k8_hyper_reduce", st);
+        k_hyper_partial<<<dim3(a.n_rb, n_chains), 256, 0, st>>>(a);
+        k_hyper_final<<<n_chains, 256, 0, st>>>(a);
+    }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }

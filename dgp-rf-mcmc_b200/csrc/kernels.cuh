@@ -36,7 +36,10 @@ struct HypArgs {
     const float* log_inv_ls; int64_t h_cs;
     float* gH; int64_t gh_cs;
     int64_t off_log_amp, off_log_inv_ls, off_mean;
+    float* part; int64_t part_cs;     // [C][row blocks][2 d + 1] partial sums (workspace)
+    int32_t n_rb, rows_per;           // filled by the launcher
 };
+int dgprf_hyper_row_blocks(int B);
 
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_fwd_tc_supported(const FwdArgs& a);
@@ -47,7 +50,7 @@ int64_t dgprf_fwd_tc2_wt_floats(int F, int g);
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
-bool dgprf_bwd_tc2_shape_ok(int B, int M, int g, int d_prev, int CS, int RS);
+bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper);
 int64_t dgprf_bwd_tc2_wp_floats(int F);
 bool dgprf_bwd_tc2_supported(const BwdArgs& a);
 int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st);

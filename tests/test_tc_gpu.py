@@ -153,3 +153,34 @@ def test_pipelined_cases_run_the_pipelined_kernels(name):
     assert "k1_fwd_tc2" in names, names
     assert "k2_bwd_tc2" in names, names
     assert "k1_fwd_simt" not in names and "k2_bwd_simt" not in names, names
+
+
+@pytest.mark.parametrize("name", ["pipelined_rbf_mean", "pipelined_arc_wide", "pipelined_kb3_g40", "protein_full_layer"])
+def test_tc_hyper_gradients(name):
+    """Hyper-parameter gradients (full-Bayes dU/dtheta and the stochastic-EM M-step) in tf32 mode: the pipelined backward
+    forms T for all input columns (one or two z passes) and writes the raw T / R slabs of the hyper reduction.
+    Stated bound: 3e-3 like the W gradients, except the scalar d log_amp = sum(dF * F), a sum with cancellation over
+    tf32-rounded F, which is held to 1e-2."""
+    model, X, Y = build(name)
+    model.set_precision("tf32")
+    p = oracle_params(model)
+    N = 5000
+    kinds = CASES[name][6] or []
+    last = f"W_{CASES[name][3] - 1}"
+    u_ref, g_ref = O.grads_autograd(p, X.double(), Y.double(), N, True)
+    u, g = model.grad_U(X, Y, N, full_bayesian=True)
+    assert float(u) == pytest.approx(float(u_ref), rel=TF32_TOL)
+    for n, ref in g_ref.items():
+        tol = ARC_UPSTREAM_GRAD_TOL if ("ARC" in kinds and n != last) else (1e-2 if n.startswith("log_amp") else TF32_TOL)
+        assert rel_err(g[n], ref) < tol, n
+    q, gq = O.em_q_and_grads(p, [p.W], X.double(), Y.double(), N)
+    u, g = model.grad_U(X, Y, N, full_bayesian=False, allow_gradient_from_W=False, hyper=True)
+    assert float(u) == pytest.approx(-float(q), rel=TF32_TOL)
+    for n, ref in gq.items():
+        tol = ARC_UPSTREAM_GRAD_TOL if "ARC" in kinds else (1e-2 if n.startswith("log_amp") else TF32_TOL)
+        assert rel_err(g[n], ref) < tol, n
+    if name.startswith("pipelined"):
+        _ffi.profile_start()
+        model.grad_U(X, Y, N, full_bayesian=True)
+        names = [nm for nm, _ in _ffi.profile_stop()]
+        assert "k2_bwd_tc2" in names, names
