@@ -73,6 +73,15 @@ __device__ __forceinline__ float slab_load(const SlabMat& m, int chain, int64_t 
     return v;
 }
 
+// slab_load with a runtime loop over the slabs (same summation order, so bit-identical): for kernels whose per-element
+// work is small, the 16-way predicated unroll of slab_load costs more issue slots than the loads it overlaps
+__device__ __forceinline__ float slab_load_rt(const SlabMat& m, int chain, int64_t row, int col) {
+    const float* p = m.ptr + chain * m.cs + row * m.ld + col;
+    float v = __ldg(p);
+    for (int s = 1; s < m.n_slabs; ++s) v += __ldg(p + s * m.ss);
+    return v;
+}
+
 struct FwdArgs {
     int32_t kind, B, d_prev, d_x, d, M, g, F, CS, ldx, do_gemm2, has_mean, tile_cols;
     SlabMat Fprev;                       // previous GP-layer output (partial slabs), ld = d_prev

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
     __shared__ float red[32];
     const int chain = blockIdx.y;
     const float* Y = a.Y + chain * a.y_cs;
-    const int64_t row_begin = (int64_t)blockIdx.x * kLikThreads + threadIdx.x, row_step = (int64_t)gridDim.x * kLikThreads;
+    const int64_t row_begin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, row_step = (int64_t)gridDim.x * blockDim.x;
     float ll_acc = 0.f, g_acc = 0.f;
 
     if (a.likelihood == DGPRF_LIK_GAUSSIAN) {
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
         for (int64_t row = row_begin; row < a.B; row += row_step) {
             float ll = 0.f, se = 0.f;
             for (int j = 0; j < a.D; ++j) {
-                const float f = slab_load(a.F, chain, row, j);
+                const float f = slab_load_rt(a.F, chain, row, j);
                 const float r = __ldg(Y + row * a.D + j) - f;
                 const float q = r * r * inv_var;
                 ll += -0.5f * (DGPRF_LOG_2PI + llv + q);
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
             int arg = 0;
 #pragma unroll 1
             for (int j = 0; j < a.D; ++j) {
-                f[j] = slab_load(a.F, chain, row, j);
+                f[j] = slab_load_rt(a.F, chain, row, j);
                 if (f[j] > mx) { mx = f[j]; arg = j; }     // first maximum, like tf.argmax
             }
             float se = 0.f;
@@ -94,12 +94,13 @@ __global__ void __launch_bounds__(64) k3_loglik_final(const LikArgs a, int nblk)
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st) {
     DGPRF_REQUIRE(a.likelihood == DGPRF_LIK_GAUSSIAN || a.D <= kMaxClasses,
                   "softmax with %d classes > %d unsupported", a.D, kMaxClasses);
-    int nblk = 1;
-    if (a.part != nullptr && a.B > 4 * kLikThreads) {
-        nblk = ceil_div(a.B, 2 * kLikThreads);
+    int nblk = 1, threads = kLikThreads;
+    if (a.part != nullptr && a.B > 256) {                  // one row per thread, up to 64 CTAs per chain
+        threads = 256;
+        nblk = ceil_div(a.B, threads);
         if (nblk > 64) nblk = 64;
     }
-    { ProfScope _ps("k3_loglik", st); k3_loglik<<<dim3(nblk, n_chains), kLikThreads, 0, st>>>(a); }
+    { ProfScope _ps("k3_loglik", st); k3_loglik<<<dim3(nblk, n_chains), threads, 0, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (nblk > 1 && (a.ll_sum || a.g_lik_log_var)) {
         k3_loglik_final<<<n_chains, 64, 0, st>>>(a, nblk);

@@ -304,6 +304,20 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
     const float* X = a.X + chain * a.x_cs;
     const float* Y = a.Y + chain * a.y_cs;
 
+    // Warm L2 with every layer's operands (z, W) once, spread over the grid: after an L2 flush (or the first step) each
+    // later phase would otherwise pay its own HBM round trip on first touch.
+    if (a.prefetch_w) {
+        const int64_t gtid = (int64_t)blockIdx.x * kST + tid, gthreads = (int64_t)gridDim.x * kST;
+        for (int l = 0; l < a.n_layers; ++l) {
+            const StepRowsLayer& y = a.layer[l];
+            const int F = y.kind == DGPRF_KIND_RBF ? 2 * y.M : y.M;
+            const float* zz = y.z + chain * y.z_cs;
+            const float* ww = y.W + chain * a.w_cs;
+            const int64_t nz = ((int64_t)(y.d_prev + y.d_x) * y.M + 31) / 32, nw = ((int64_t)F * y.g + 31) / 32;   // 128-byte lines
+            for (int64_t i = gtid; i < nz; i += gthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(zz + 32 * i));
+            for (int64_t i = gtid; i < nw; i += gthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(ww + 32 * i));
+        }
+    }
     for (int e = tid; e < a.d_in * kSR; e += kST) {
         const int q = e / kSR, r = e % kSR;
         x_t[e] = (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
