@@ -72,7 +72,7 @@ struct LayerWs {
     int64_t n_phi, n_fpart, n_dpart, n_tpart, n_rpart;       // floats per chain
     size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
     int tc2;                                                 // pipelined TC forward: prepped operand buffers below
-    int64_t n_zt, n_wt; size_t zt, wt;
+    int64_t n_zt, n_wt, n_at, n_ot; size_t zt, wt, at, ot;
     int64_t n_wp; size_t wp; int bwd2;                       // pipelined TC backward: padded W rows
 };
 struct WsLayout {
@@ -152,8 +152,15 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
             s.wp = take(s.n_wp);
         }
         if (s.tc2) {
-            s.n_zt = dgprf_fwd_tc2_zt_floats(y.M);          // one copy per chain (only the first is used when z is shared)
-            s.zt = take(s.n_zt);
+            if (layer_d(y) <= 128) {
+                s.n_zt = dgprf_fwd_tc2_zt_floats(y.M);      // one copy per chain (only the first is used when z is shared)
+                s.zt = take(s.n_zt);
+            } else {                                        // WIDE variant: input and Omega^T, tf32 hi / lo
+                s.n_at = dgprf_fwd_tc2_at_floats(B, layer_d(y));
+                s.at = take(s.n_at);
+                s.n_ot = dgprf_fwd_tc2_ot_floats(y.M, layer_d(y));
+                s.ot = take(s.n_ot);
+            }
             s.n_wt = dgprf_fwd_tc2_wt_floats(layer_F(y), y.g);
             s.wt = take(s.n_wt);
         }
@@ -252,7 +259,11 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
-        if (w.L[l].tc2) { a.zt = wsf(ws, w.L[l].zt); a.wt = wsf(ws, w.L[l].wt); }
+        if (w.L[l].tc2) {
+            a.wt = wsf(ws, w.L[l].wt);
+            if (w.L[l].n_zt > 0) a.zt = wsf(ws, w.L[l].zt);
+            if (w.L[l].n_at > 0) { a.at = wsf(ws, w.L[l].at); a.ot = wsf(ws, w.L[l].ot); }
+        }
         int rc;
         if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);   // pipelined
         else if (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a)) rc = dgprf_launch_fwd_tc(a, m->n_chains, st);

@@ -92,6 +92,7 @@ struct FwdArgs {
     float* Phi;      int64_t phi_cs;     // [B, F] nullable
     float* Fpart;    int64_t fpart_cs;   // [CS][B][g]
     float* zt; int64_t zt_cs; float* wt; // pipelined TC forward: prepped z^T hi/lo [2][M][128] and W^T [NG][F] (workspace)
+    float* at; float* ot;                // ... WIDE variant: input hi/lo [2][B][Kp] and Omega^T hi/lo [2][M][Kp]
 };
 
 struct BwdArgs {

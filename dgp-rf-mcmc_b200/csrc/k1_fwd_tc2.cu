@@ -13,6 +13,10 @@
 //      the wait/poll code between the two GEMMs of a tile left it idle a third of the time)
 //     connected by mbarriers; P (D1) is double-buffered in TMEM and the z tile is a 2-stage ring (when it
 //     fits), so GEMM #1 of tile t+1 and the loads of tile t+2 run under the epilogue of tile t.
+//   * WIDE variant (input width > 128, e.g. the MNIST-shaped configs): the A operand no longer fits in tensor memory, so
+//     GEMM #1 becomes a classic K loop in SS mode: a TMA ring of k-blocks [A hi | A lo | Omega hi | Omega lo] where A is the
+//     raw layer input and Omega = exp(log_inv_ls) * z + mean (both split into tf32 hi/lo by prep kernels), so neither the
+//     per-row scaling nor the mean bias is needed in the kernel; epilogue, GEMM #2 and the Phi store are unchanged;
 //   * the streamed operands are pre-laid for TMA by a small prep kernel per launch: z^T split into tf32
 //     hi/lo, K-major, zero-padded to 128 K columns ([2][M][128]) and W^T rounded to tf32 ([NG][F]).
 #include <stdio.h>
@@ -27,7 +31,8 @@ constexpr int V2_HDR = 1024;                      // bias row + mbarriers + TMEM
 constexpr int V2_BLK = V2_BM * 128;               // [128 x 32 tf32] block
 constexpr int V2_BBLK = V2_BN * 128;              // [64 x 32 tf32] block
 constexpr int V2_KB = 4;                          // K blocks of GEMM #1 (input width <= 128)
-constexpr uint32_t V2_TMEM_COLS = 512;            // A_hi 128 | A_lo 128 | D1 2x64 | D2 64
+constexpr uint32_t V2_TMEM_COLS = 512;            // A_hi 128 | A_lo 128 | D1 2x64 | D2 64   (WIDE: D1 2x64 | D2 64 only)
+constexpr int V2_RING = 2 * V2_BLK + 2 * V2_BBLK; // WIDE k-block slot: A hi 16K | A lo 16K | Omega hi 8K | Omega lo 8K
 
 namespace tc {
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -78,27 +83,29 @@ __device__ __forceinline__ void issue_gemm2(uint32_t tm_d2, uint64_t dphi, uint6
                           (b | k4) != 0 ? 1u : acc_first);
 }
 
-template <int NG>
+template <int NG, bool WIDE>
 __global__ void __launch_bounds__(V2_THREADS, 1)
-k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
-           const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt) {
+k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW, long long* const tl, const __grid_constant__ CUtensorMap map_cos,
+           const __grid_constant__ CUtensorMap map_sin, const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt,
+           const __grid_constant__ CUtensorMap map_at) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* bias_s = reinterpret_cast<float*>(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_BM * sizeof(float));
     uint8_t* sPhi = sm + V2_HDR;                         // 4 blocks [128 x 32]: cos 0,1 | sin 2,3
-    uint8_t* sW = sPhi + 4 * V2_BLK;                     // 2 stages x 4 blocks [NG x 32]
-    uint8_t* sB1 = sW + 2 * 4 * NG * 128;                // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
-    uint64_t* b1_full = bars + 0;     // [2] TMA complete_tx      -> MMA
-    uint64_t* b1_empty = bars + 2;    // [2] MMA commit           -> producer
-    uint64_t* d1_full = bars + 4;     // [2] MMA commit           -> epilogue
-    uint64_t* d1_empty = bars + 6;    // [2] epilogue (8 warps)   -> MMA
-    uint64_t* phi_full = bars + 8;    // epilogue (8 warps)       -> MMA, store
-    uint64_t* phi_empty = bars + 9;   // MMA commit + store warp  -> epilogue      (count 2)
-    uint64_t* w_full = bars + 10;     // [2] TMA complete_tx      -> MMA
-    uint64_t* w_empty = bars + 12;    // [2] MMA commit           -> producer
-    uint64_t* d2_full = bars + 14;    // MMA commit               -> final epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint8_t* sW = sPhi + 4 * V2_BLK;                     // NSW stages x 4 blocks [NG x 32]
+    uint8_t* sB1 = sW + NSW * 4 * NG * 128;              // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
+                                                         // WIDE: NS1 k-block slots of V2_RING bytes
+    uint64_t* b1_full = bars + 0;     // [3] TMA complete_tx      -> MMA
+    uint64_t* b1_empty = bars + 3;    // [3] MMA commit           -> producer
+    uint64_t* d1_full = bars + 6;     // [2] MMA commit           -> epilogue
+    uint64_t* d1_empty = bars + 8;    // [2] epilogue warps       -> MMA
+    uint64_t* phi_full = bars + 10;   // epilogue warps           -> MMA, store
+    uint64_t* phi_empty = bars + 11;  // MMA commit + store warp  -> epilogue      (count 2)
+    uint64_t* w_full = bars + 12;     // [2] TMA complete_tx      -> MMA
+    uint64_t* w_empty = bars + 14;    // [2] MMA commit           -> producer
+    uint64_t* d2_full = bars + 16;    // MMA commit               -> final epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chain = blockIdx.z, cs = blockIdx.y, row0 = blockIdx.x * V2_BM;
@@ -117,13 +124,15 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
     const int n_my = ct0 < n_ct ? min(per, n_ct - ct0) : 0;
     const int n_kb = (a.d + 31) / 32;
     const int nb2 = rbf ? 4 : 2;
-    const uint32_t b1_stage = 2u * n_kb * V2_BBLK;
+    const uint32_t b1_stage = WIDE ? (uint32_t)V2_RING : 2u * n_kb * V2_BBLK;
 
     if (warp == V2_EPI_WARPS) tc::tmem_alloc(tmem_slot, V2_TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             tc::mbar_init(b1_full + i, 1);
             tc::mbar_init(b1_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             tc::mbar_init(d1_full + i, 1);
             tc::mbar_init(d1_empty + i, V2_EPI_WARPS);
             tc::mbar_init(w_full + i, 1);
@@ -138,11 +147,11 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_ahi = tmem_base, tm_alo = tmem_base + 128, tm_d1 = tmem_base + 256, tm_d2 = tmem_base + 384;
+    const uint32_t tm_ahi = tmem_base, tm_alo = tmem_base + 128, tm_d1 = tmem_base + (WIDE ? 0 : 256), tm_d2 = tmem_base + (WIDE ? 128 : 384);
 
     // ---- A operand -> TMEM.  The 128-row input tile is first read coalesced into shared memory (it borrows the
     //      Phi / W regions, idle until the pipeline starts), then each epilogue thread owns one row x 64 K columns.
-    {
+    if (!WIDE) {
         float* sIn = reinterpret_cast<float*>(sPhi);          // [128][129]
         float* sSq = reinterpret_cast<float*>(sB1);           // [128] exp(log_inv_ls) | [128] mean
         float* sMean = sSq + 128;
@@ -219,7 +228,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
         // ===================================== EPILOGUE =====================================
         const int lq = warp & 3, cq = warp >> 2;               // TMEM lane quarter, 16-column quarter of the tile
         const int r = 32 * lq + lane;
-        const float bias = a.has_mean ? bias_s[r] : 0.f;
+        const float bias = (!WIDE && a.has_mean) ? bias_s[r] : 0.f;     // WIDE: the mean is folded into Omega
         const int pb = cq >> 1, pc = (cq & 1) * 4;             // 32-column Phi block and first 16-byte chunk inside it
         for (int t = 0; t < n_my; ++t) {
             const int c0 = (ct0 + t) * V2_BN;
@@ -287,6 +296,35 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
         // The whole warp walks the loop converged (waits included); one elected lane issues.  Descriptors are
         // built once: advancing along K or to another block only adds to the 14-bit start-address field.
         const uint64_t dB1 = tc::make_desc_sw128(tc::smem_u32(sB1));
+        if (WIDE) {
+            // K loop in SS mode: k-block `it` (counted over all tiles of the CTA) lives in ring slot it % NS1
+            int it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int buf = t & 1;
+                tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
+                if (lane == 0) TL(t, 5);
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int slot = it % NS1;
+                    tc::mbar_wait(b1_full + slot, (it / NS1) & 1);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint64_t dah = dB1 + ((slot * b1_stage) >> 4), dal = dah + (V2_BLK >> 4);
+                        const uint64_t doh = dah + ((2 * V2_BLK) >> 4), dol = doh + (V2_BBLK >> 4);
+                        const uint32_t dcol = tm_d1 + 64 * buf;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            tc::umma_tf32(dcol, dal + 2 * k4, doh + 2 * k4, IDESC1, k4 != 0 ? 1u : (kb != 0 ? 1u : 0u));
+                            tc::umma_tf32(dcol, dah + 2 * k4, dol + 2 * k4, IDESC1, 1u);
+                            tc::umma_tf32(dcol, dah + 2 * k4, doh + 2 * k4, IDESC1, 1u);
+                        }
+                        tc::umma_commit(b1_empty + slot);              // k-block consumed
+                        if (kb == n_kb - 1) tc::umma_commit(d1_full + buf);   // P ready
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) TL(t, 6);
+            }
+        } else
         for (int t = 0; t < n_my; ++t) {
             const int buf = t & 1;
             const int s1 = t % NS1;
@@ -315,9 +353,9 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
         const uint64_t dPhi = tc::make_desc_sw128(tc::smem_u32(sPhi));
         const uint64_t dW = tc::make_desc_sw128(tc::smem_u32(sW));
         for (int u = 0; u < n_my; ++u) {
-            const int ws = u & 1;
+            const int ws = u % NSW;
             tc::mbar_wait(phi_full, u & 1);
-            if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u >> 1) & 1);
+            if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u / NSW) & 1);
             if (lane == 0) TL(u, 7);
             tc::tc_fence_after();
             if (tc::elect_one()) {
@@ -337,8 +375,23 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
         // ===================================== TMA PRODUCER =====================================
         if (tc::elect_one()) {
             const int zc = a.zt_cs != 0 ? chain : 0;
+            int it = 0;
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (ct0 + t) * V2_BN;
+                if (WIDE) {
+                    // ---- k-blocks of this tile: [A hi | A lo] rows row0.. of the input, [Omega hi | Omega lo] feature rows c0.. ----
+                    for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                        const int slot = it % NS1;
+                        tc::mbar_wait(b1_empty + slot, ((it / NS1) & 1) ^ 1);
+                        if (kb == 0) TL(t, 9);
+                        tc::mbar_expect_tx(b1_full + slot, b1_stage);
+                        const uint32_t sl = tc::smem_u32(sB1) + slot * b1_stage;
+                        tc::tma_load_3d(&map_at, sl, b1_full + slot, 32 * kb, row0, 2 * chain);
+                        tc::tma_load_3d(&map_at, sl + V2_BLK, b1_full + slot, 32 * kb, row0, 2 * chain + 1);
+                        tc::tma_load_3d(&map_zt, sl + 2 * V2_BLK, b1_full + slot, 32 * kb, c0, 2 * chain);
+                        tc::tma_load_3d(&map_zt, sl + 2 * V2_BLK + V2_BBLK, b1_full + slot, 32 * kb, c0, 2 * chain + 1);
+                    }
+                } else {
                 // ---- z tile (B of GEMM #1): rows = feature columns, K-major, tf32 hi blocks then lo blocks ----
                 const int s1 = t % NS1;
                 tc::mbar_wait(b1_empty + s1, ((t / NS1) & 1) ^ 1);
@@ -349,10 +402,11 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, long long* const tl, const __grid_con
                     tc::tma_load_3d(&map_zt, b1 + kb * V2_BBLK, b1_full + s1, 32 * kb, c0, 2 * zc);
                     tc::tma_load_3d(&map_zt, b1 + (n_kb + kb) * V2_BBLK, b1_full + s1, 32 * kb, c0, 2 * zc + 1);
                 }
+                }
                 // ---- W^T tile (B of GEMM #2) into ring stage t & 1 ----
                 if (a.do_gemm2) {
-                    const int ws = t & 1;
-                    tc::mbar_wait(w_empty + ws, ((t >> 1) & 1) ^ 1);
+                    const int ws = t % NSW;
+                    tc::mbar_wait(w_empty + ws, ((t / NSW) & 1) ^ 1);
                     TL(t, 10);
                     tc::mbar_expect_tx(w_full + ws, (uint32_t)nb2 * NG * 128);
                     for (int b = 0; b < nb2; ++b)
@@ -424,8 +478,114 @@ k_prep_tc2(const float* __restrict__ z, int64_t z_cs, int d, int M, float* __res
         if (j0 + i < NG && f0 + tx < F) o[(int64_t)(j0 + i) * F + f0 + tx] = tc::to_tf32(tile[tx][i]);
 }
 
+// ---- WIDE operand prep ------------------------------------------------------------------------------------------
+// at [2][B][Kp]: the layer input (previous layer's output slabs summed in slab order | model input), tf32 hi / lo, zero padded
+__global__ void __launch_bounds__(256)
+k_prep_wide_a(const FwdArgs a, int Kp, float* __restrict__ at) {
+    const int chain = blockIdx.y;
+    const int64_t n = (int64_t)a.B * Kp;
+    const float* X = a.X + chain * a.x_cs;
+    const float* fp = a.Fprev.ptr + chain * a.Fprev.cs;
+    float* hi = at + (int64_t)chain * 2 * n;
+    float* lo = hi + n;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int64_t row = i / Kp;
+        const int q = (int)(i % Kp);
+        float v = 0.f;
+        if (q < a.d_prev) {
+            v = __ldg(fp + row * a.Fprev.ld + q);
+            for (int sl = 1; sl < a.Fprev.n_slabs; ++sl) v += __ldg(fp + sl * a.Fprev.ss + row * a.Fprev.ld + q);
+        } else if (q < a.d) {
+            v = __ldg(X + row * a.ldx + (q - a.d_prev));
+        }
+        const float h = tc::to_tf32(v);
+        hi[i] = h;
+        lo[i] = tc::to_tf32(v - h);
+    }
+}
+// ot [2][M][Kp]: Omega^T = (exp(log_inv_ls) * z + mean)^T, tf32 hi / lo, K-major, zero padded (layers/rf_layers.py: Omega)
+__global__ void __launch_bounds__(256)
+k_prep_wide_o(const FwdArgs a, int Kp, float* __restrict__ ot) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int chain = blockIdx.z;
+    const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const float* zz = a.z + chain * a.z_cs;
+    const float* ls = a.log_inv_ls + chain * a.h_cs;
+    const float* mean = a.has_mean ? a.mean + chain * a.h_cs : nullptr;
+    for (int i = ty; i < 32; i += 8) {
+        const int q = k0 + i;
+        float v = 0.f;
+        if (q < a.d && m0 + tx < a.M) {
+            v = expf(__ldg(ls + q)) * __ldg(zz + (int64_t)q * a.M + m0 + tx);
+            if (mean != nullptr) v += __ldg(mean + q);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    float* hi = ot + (int64_t)chain * 2 * a.M * Kp;
+    float* lo = hi + (int64_t)a.M * Kp;
+    for (int i = ty; i < 32; i += 8)
+        if (m0 + i < a.M) {
+            const float v = tile[tx][i];
+            const float h = tc::to_tf32(v);
+            hi[(int64_t)(m0 + i) * Kp + k0 + tx] = h;
+            lo[(int64_t)(m0 + i) * Kp + k0 + tx] = tc::to_tf32(v - h);
+        }
+}
+
 static size_t tc2_smem_bytes(int NG, int n_kb, int ns1) {
     return 1024 + V2_HDR + 4 * (size_t)V2_BLK + 2 * 4 * (size_t)NG * 128 + (size_t)ns1 * 2 * n_kb * V2_BBLK;
+}
+static size_t tc2_wide_smem_bytes(int NG, int nsw, int ns) {
+    return 1024 + V2_HDR + 4 * (size_t)V2_BLK + (size_t)nsw * 4 * NG * 128 + (size_t)ns * V2_RING;
+}
+
+template <int NG>
+static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) {
+    const int Kp = (a.d + 31) & ~31;
+    const int nsw = NG >= 32 ? 1 : 2;
+    int ns = 3;
+    while (ns > 1 && tc2_wide_smem_bytes(NG, nsw, ns) > 232448) --ns;
+    const size_t smem = tc2_wide_smem_bytes(NG, nsw, ns);
+    static bool configured = false;
+    if (!configured) {
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    DGPRF_REQUIRE(a.at != nullptr && a.ot != nullptr && a.wt != nullptr, "wide pipelined forward needs the prepped operand buffers");
+    {
+        ProfScope _ps("k_prep_tc2_wide", st);
+        int blocks = ceil_div((int64_t)a.B * Kp, 256 * 4);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_prep_wide_a<<<dim3(blocks, n_chains), 256, 0, st>>>(a, Kp, a.at);
+        k_prep_wide_o<<<dim3(ceil_div(a.M, 32), Kp / 32, n_chains), 256, 0, st>>>(a, Kp, a.ot);
+        const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
+        k_prep_tc2<<<dim3(n_wt_tiles, n_chains), 256, 0, st>>>(a.z, a.z_cs, a.d, a.M, nullptr, 0, a.W, a.w_cs, a.F, a.g, NG, a.wt, (int64_t)NG * a.F);
+        DGPRF_CHECK_CUDA(cudaGetLastError());
+    }
+    CUtensorMap mc, ms, mo, mw, ma;
+    memset(&mc, 0, sizeof(mc));
+    memset(&ms, 0, sizeof(ms));
+    if (a.Phi != nullptr) {
+        int rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+        if (rc) return rc;
+        if (a.kind == DGPRF_KIND_RBF) {
+            rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+            if (rc) return rc;
+        }
+    }
+    int rc = dgprf_make_tmap_3d(&mo, a.ot, Kp, a.M, 2 * n_chains, Kp, (uint64_t)a.M * Kp, V2_BN);
+    if (rc) return rc;
+    rc = dgprf_make_tmap_3d(&ma, a.at, Kp, a.B, 2 * n_chains, Kp, (uint64_t)a.B * Kp, V2_BM);
+    if (rc) return rc;
+    rc = dgprf_make_tmap_3d(&mw, a.wt, a.F, NG, n_chains, a.F, (uint64_t)NG * a.F, NG);
+    if (rc) return rc;
+    static long long* tl = nullptr;
+    dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
+    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw, tl, mc, ms, mo, mw, ma); }
+    DGPRF_CHECK_CUDA(cudaGetLastError());
+    return DGPRF_OK;
 }
 
 template <int NG>
@@ -435,7 +595,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const size_t smem = tc2_smem_bytes(NG, n_kb, ns1);
     static bool configured = false;
     if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
@@ -469,7 +629,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG><<<grid, V2_THREADS, smem, st>>>(b, ns1, tl, mc, ms, mz, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2, tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12];
@@ -490,25 +650,39 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
 // number of column splits (CTAs per row block; each walks M/64/splits column tiles) or 0 when the layered v1
 // kernel should run instead: the per-CTA prologue and pipeline fill only pay off over >= 4 tiles per CTA.
 int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains) {
-    if (tile_cols != 64 || d > 128 || (M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
+    if (tile_cols != 64 || (M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
     const int n_ct = ceil_div(M, V2_BN);
     const int64_t rb = (int64_t)ceil_div(B, V2_BM) * n_chains;
     int cs = (int)((4 * 148 + rb - 1) / rb);                   // >= 4 waves of CTAs when the problem allows
     if (cs > kMaxCS) cs = kMaxCS;
     if (cs > n_ct) cs = n_ct;
     if (cs < 1) cs = 1;
+    if (d > 128) {
+        // WIDE variant: every tile is a K loop of d/32 k-blocks, so one tile per CTA already amortises the start-up;
+        // the operand buffers hold the input / Omega split in two, which bounds the size this path is taken for
+        if (getenv("DGPRF_NO_TC2_WIDE") != nullptr || (int64_t)B * ((d + 31) & ~31) * n_chains > ((int64_t)1 << 28)) return 0;
+        return cs;
+    }
     while (cs > 1 && n_ct / cs < 4) --cs;
     return n_ct / cs >= 4 ? cs : 0;
 }
 bool dgprf_fwd_tc2_supported(const FwdArgs& a) {
-    return a.zt != nullptr && a.wt != nullptr && (a.Phi == nullptr || (a.phi_cs % 4) == 0);
+    return a.wt != nullptr && (a.d <= 128 ? a.zt != nullptr : (a.at != nullptr && a.ot != nullptr)) &&
+           (a.Phi == nullptr || (a.phi_cs % 4) == 0);
 }
+int64_t dgprf_fwd_tc2_at_floats(int B, int d) { return d > 128 ? 2 * (int64_t)B * ((d + 31) & ~31) : 0; }
+int64_t dgprf_fwd_tc2_ot_floats(int M, int d) { return d > 128 ? 2 * (int64_t)M * ((d + 31) & ~31) : 0; }
 // floats of the prepped operand buffers: zt per spectral-draw copy, wt per chain
 int64_t dgprf_fwd_tc2_zt_floats(int M) { return 2 * (int64_t)M * 128; }
 int64_t dgprf_fwd_tc2_wt_floats(int F, int g) { return (int64_t)(g <= 16 ? 16 : g <= 32 ? 32 : 64) * F; }
 
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const int g = a.g;
+    if (a.d > 128) {
+        if (g <= 16) return launch_fwd_tc2_wide<16>(a, n_chains, st);
+        if (g <= 32) return launch_fwd_tc2_wide<32>(a, n_chains, st);
+        return launch_fwd_tc2_wide<64>(a, n_chains, st);
+    }
     if (g <= 16) return launch_fwd_tc2<16>(a, n_chains, st);
     if (g <= 32) return launch_fwd_tc2<32>(a, n_chains, st);
     return launch_fwd_tc2<64>(a, n_chains, st);

@@ -46,6 +46,8 @@ bool dgprf_fwd_tc_supported(const FwdArgs& a);
 bool dgprf_fwd_tc2_supported(const FwdArgs& a);
 int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains);
 int64_t dgprf_fwd_tc2_zt_floats(int M);
+int64_t dgprf_fwd_tc2_at_floats(int B, int d);
+int64_t dgprf_fwd_tc2_ot_floats(int M, int d);
 int64_t dgprf_fwd_tc2_wt_floats(int F, int g);
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
