@@ -482,25 +482,36 @@ k_prep_tc2(const float* __restrict__ z, int64_t z_cs, int d, int M, float* __res
 // at [2][B][Kp]: the layer input (previous layer's output slabs summed in slab order | model input), tf32 hi / lo, zero padded
 __global__ void __launch_bounds__(256)
 k_prep_wide_a(const FwdArgs a, int Kp, float* __restrict__ at) {
+    // grid (row blocks of 8 rows, chains); a thread converts 4 consecutive K columns of one row per step (float4 stores)
     const int chain = blockIdx.y;
     const int64_t n = (int64_t)a.B * Kp;
     const float* X = a.X + chain * a.x_cs;
     const float* fp = a.Fprev.ptr + chain * a.Fprev.cs;
     float* hi = at + (int64_t)chain * 2 * n;
     float* lo = hi + n;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const int64_t row = i / Kp;
-        const int q = (int)(i % Kp);
-        float v = 0.f;
-        if (q < a.d_prev) {
-            v = __ldg(fp + row * a.Fprev.ld + q);
-            for (int sl = 1; sl < a.Fprev.n_slabs; ++sl) v += __ldg(fp + sl * a.Fprev.ss + row * a.Fprev.ld + q);
-        } else if (q < a.d) {
-            v = __ldg(X + row * a.ldx + (q - a.d_prev));
+    const int k4n = Kp >> 2;                               // float4 per row
+    const int r_in = threadIdx.x / 32, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + r_in; row < a.B; row += (int64_t)gridDim.x * 8) {
+        for (int k4 = lane; k4 < k4n; k4 += 32) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = 4 * k4 + i;
+                float x = 0.f;
+                if (q < a.d_prev) {
+                    x = __ldg(fp + row * a.Fprev.ld + q);
+                    for (int sl = 1; sl < a.Fprev.n_slabs; ++sl) x += __ldg(fp + sl * a.Fprev.ss + row * a.Fprev.ld + q);
+                } else if (q < a.d) {
+                    x = __ldg(X + row * a.ldx + (q - a.d_prev));
+                }
+                v[i] = x;
+            }
+            float4 h, l;
+            h.x = tc::to_tf32(v[0]); h.y = tc::to_tf32(v[1]); h.z = tc::to_tf32(v[2]); h.w = tc::to_tf32(v[3]);
+            l.x = tc::to_tf32(v[0] - h.x); l.y = tc::to_tf32(v[1] - h.y); l.z = tc::to_tf32(v[2] - h.z); l.w = tc::to_tf32(v[3] - h.w);
+            *reinterpret_cast<float4*>(hi + row * Kp + 4 * k4) = h;
+            *reinterpret_cast<float4*>(lo + row * Kp + 4 * k4) = l;
         }
-        const float h = tc::to_tf32(v);
-        hi[i] = h;
-        lo[i] = tc::to_tf32(v - h);
     }
 }
 // ot [2][M][Kp]: Omega^T = (exp(log_inv_ls) * z + mean)^T, tf32 hi / lo, K-major, zero padded (layers/rf_layers.py: Omega)
@@ -556,8 +567,8 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     DGPRF_REQUIRE(a.at != nullptr && a.ot != nullptr && a.wt != nullptr, "wide pipelined forward needs the prepped operand buffers");
     {
         ProfScope _ps("k_prep_tc2_wide", st);
-        int blocks = ceil_div((int64_t)a.B * Kp, 256 * 4);
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        int blocks = ceil_div(a.B, 8);
+        if (blocks > 148 * 16) blocks = 148 * 16;
         k_prep_wide_a<<<dim3(blocks, n_chains), 256, 0, st>>>(a, Kp, a.at);
         k_prep_wide_o<<<dim3(ceil_div(a.M, 32), Kp / 32, n_chains), 256, 0, st>>>(a, Kp, a.ot);
         const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
