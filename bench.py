@@ -174,7 +174,7 @@ def run_ours(args, rank, world):
     B, N = CFG["batch"], CFG["N"]
     nb = N // B
     kw = dict(lr=CFG["lr"], momentum_decay=CFG["momentum_decay"], temperature=CFG["temperature"])
-    launches_per_step = 1 if args.precision == "fp32" else 2 * CFG["L"] + 2     # row-fused step with fused update | layered
+    launches_per_step = 1                 # refined below from the library's event hook (fp32: the row-fused step is one launch)
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -254,6 +254,7 @@ def run_ours(args, rank, world):
         for i in range(PROF_STEPS):
             step(i)
         recs = _ffi.profile_stop()
+        launches_per_step = max(1, len(recs) // PROF_STEPS)          # launches the library's event hook saw per step
         per = {}
         for idx, (nm, ms) in enumerate(recs):
             per.setdefault((nm, idx % launches_per_step), []).append(ms)
@@ -261,30 +262,33 @@ def run_ours(args, rank, world):
         step_us = sum(k["avg_us"] for k in kernels)
         fwd_f, bwd_f = algorithmic_flops(e.spec, B)
         L = CFG["L"]
-        for k in kernels:
-            s = k["slot"]
-            if launches_per_step == 1:
+        n_fwd = n_bwd = 0
+        for k in kernels:                                            # in launch order: forward layers up, backward layers down
+            nm = k["kernel"]
+            if nm.startswith("k9_"):
                 k["flops"] = sum(fwd_f) + sum(bwd_f)
                 k["what"] = "row-fused step: forward + likelihood seed + backward (all layers) + grid barrier + update"
-            elif s < L:
-                k["flops"] = fwd_f[s]; k["what"] = f"fwd layer {s}"
-            elif s == L:
-                k["what"] = "likelihood seed"
-            elif s <= 2 * L:
-                l = 2 * L - s
-                k["flops"] = bwd_f[l]; k["what"] = f"bwd layer {l}"
-            else:
+            elif nm.startswith("k1_fwd"):
+                k["flops"] = fwd_f[min(n_fwd, L - 1)]; k["what"] = f"fwd layer {n_fwd}"; n_fwd += 1
+            elif nm.startswith("k2_bwd"):
+                l = max(L - 1 - n_bwd, 0)
+                k["flops"] = bwd_f[l]; k["what"] = f"bwd layer {l}"; n_bwd += 1
+            elif nm.startswith("k5_"):
                 k["bytes"] = 20.0 * e.layout.w_len; k["what"] = "sgmcmc update"
+            elif nm.startswith("k3_"):
+                k["what"] = "likelihood seed"
+            else:
+                k["what"] = "operand prep"
             k["share"] = k["avg_us"] / step_us
-        dom = max(kernels, key=lambda k: k["avg_us"])
+        dom = max((k for k in kernels if "flops" in k or "bytes" in k), key=lambda k: k["avg_us"])
         tf32_peak = pk["bf16_tflops"] / 2.0
         if "flops" in dom:
             ach = dom["flops"] / (dom["avg_us"] * 1e-6) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                     "traffic": None, "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
                     "peak_source": f"{pk_src} bf16 burst / 2 (kind::tf32 rate)",
-                    "note": "configs[1] is latency-bound (0.18 GFLOP per step): see roofline_k5_256MiB and DESIGN.md section 5 "
-                            "for the kernels at bandwidth/throughput-relevant sizes"}
+                    "note": "configs[1] is latency / issue bound (0.18 GFLOP and 0.4 MB of parameters per step): roofline_tc_layer and "
+                            "roofline_k5_256MiB in this line give the tensor-core and update kernels at throughput-relevant sizes"}
         else:
             ach = dom["bytes"] / (dom["avg_us"] * 1e-6) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
