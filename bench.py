@@ -285,7 +285,9 @@ def run_ours(args, rank, world):
         if "flops" in dom:
             ach = dom["flops"] / (dom["avg_us"] * 1e-6) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                    "traffic": None, "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
+                    "traffic": (408576.0 if dom["kernel"].startswith("k9_") else None),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on this workload (profiles/r01_ncu_full_summary.md section E)",
+                    "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
                     "peak_source": f"{pk_src} bf16 burst / 2 (kind::tf32 rate)",
                     "note": "configs[1] is latency / issue bound (0.18 GFLOP and 0.4 MB of parameters per step): roofline_tc_layer and "
                             "roofline_k5_256MiB in this line give the tensor-core and update kernels at throughput-relevant sizes"}
@@ -370,6 +372,8 @@ def run_ours(args, rank, world):
             "workload": f"one [RF->GP] layer at configs[4] scale: B={tB}, d={td}, M={tM}, n_gp={tg}, RBF, tf32 mode",
             "tf32_peak_tflops": tf32_peak, "hbm_copy_peak_gbs": pk["hbm_gbs"], "hbm_write_only_gbs": hbm_write_gbs,
             "peak_source": pk_src + " (copy, bf16); write-only measured live with a 1 GiB fill",
+            "traffic_ncu_bytes": {"fwd": 2.104e9 + 84.0e6, "bwd": 2.166e9 + 4.2e6, "algorithmic_phi_bytes": phi_bytes,
+                                  "source": "ncu --set full, profiles/r01_ncu_full_summary.md section E"},
             "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * 128 * tM + tF * tg),
                             "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored (TMA): bound by the write stream",
                             hbm_write_gbs, "write-only"),
