@@ -34,7 +34,7 @@ struct StepRowsLayer {
 };
 
 struct StepRowsArgs {
-    int32_t n_layers, likelihood, B, d_in, d_out, dmax, Fmax, bs_cap, prefetch_w, zr_cap;
+    int32_t n_layers, likelihood, B, d_in, d_out, dmax, Fmax, bs_cap, prefetch_w, zr_cap, prefetch_bwd;
     int64_t h_cs, w_cs;
     const float* X; int64_t x_cs;
     const float* Y; int64_t y_cs;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
         const bool top = l == a.n_layers - 1;
         const bool w_ready = l > 0 && fc_max >= F && (top ? top_w_in_bs : w_prefetched);
         bool z_ready = false;
-        if (a.prefetch_w && l > 0 && a.zr_cap > 0) {
+        if (a.prefetch_bwd && l > 0 && a.zr_cap > 0) {
             z_ready = small_gemm_prefetch_z(y.z + chain * y.z_cs, M, M, y.d_prev, zr_s, a.zr_cap);
             if (z_ready) cp_async_commit();
         }
@@ -730,6 +730,7 @@ int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, c
     if (getenv("DGPRF_K9_TIMING") && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
     a.timing = dbg;
     a.prefetch_w = getenv("DGPRF_K9_NOPREFETCH") ? 0 : 1;
+    a.prefetch_bwd = (a.prefetch_w && getenv("DGPRF_K9_BWD_PREFETCH")) ? 1 : 0;
     {
         ProfScope _ps("k9_step_rows", st);
         if (a.fuse_update) {
