@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(kST, 1) k9_step_rows(const __grid_constant__ S
     // =========================== fused update (cooperative launch only) ===========================
     if (a.fuse_update) {
         grid_barrier(a.bar, my_gen, gridDim.x * gridDim.y);
+        K9_STAMP();
         const int64_t n4 = a.upd.n >> 2;
         const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;          // 128-bit vectors per CTA
         const int64_t v0 = (int64_t)grp * per, v1 = min(n4, v0 + per);
