@@ -11,6 +11,8 @@ The padding between tensors is kept at exactly zero by every kernel.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from dataclasses import dataclass, field
@@ -361,6 +363,8 @@ class Engine:
         fn, head, mid, tail = st[0], st[1], st[2], st[3]
         # pinned host tensors are read in place by the kernels (zero-copy); pageable ones go through staging copies
         zc = 1 if (X_host.is_pinned() and Y_host.is_pinned() and (u_host is None or u_host.is_pinned())) else 0
+        if zc and os.environ.get("DGPRF_NO_ZERO_COPY"):
+            zc = 0
         rc = fn(*head, X_host.data_ptr(), Y_host.data_ptr(), *mid[0], zc, *mid[1], lr, data_size, momentum_decay, temperature,
                 1 if resample else 0, seed, step, *tail, u_host.data_ptr() if u_host is not None else None,
                 torch.cuda.current_stream().cuda_stream)
