@@ -80,8 +80,8 @@ struct WsLayout {
     int RS;        // row splits of the layered backward (gW slabs)
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
-    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, total;
-    int64_t n_dfsum, n_hpart;
+    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, fsum, total;
+    int64_t n_dfsum, n_hpart, n_fsum;
 };
 
 static inline int layer_F(const dgprf_layer& l) { return l.kind == DGPRF_KIND_RBF ? 2 * l.M : l.M; }
@@ -197,6 +197,9 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     for (int l = 0; l + 1 < m->n_layers; ++l)          // pre-summed dF of a pipelined TC backward (one slab instead of CS)
         if (w->L[l].bwd2 && (int64_t)B * m->layer[l].g > w->n_dfsum) w->n_dfsum = (int64_t)B * m->layer[l].g;
     if (w->n_dfsum > 0) w->dfsum = take(w->n_dfsum);
+    for (int l = 1; l < m->n_layers; ++l)              // pre-summed F_{l-1} for a pipelined TC forward whose input comes in several slabs
+        if (w->L[l].tc2 && w->L[l - 1].CSf > 1 && (int64_t)B * m->layer[l - 1].g > w->n_fsum) w->n_fsum = (int64_t)B * m->layer[l - 1].g;
+    if (w->n_fsum > 0) w->fsum = take(w->n_fsum);
     w->total = off;
     return DGPRF_OK;
 }
@@ -265,7 +268,15 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
             if (w.L[l].n_at > 0) { a.at = wsf(ws, w.L[l].at); a.ot = wsf(ws, w.L[l].ot); }
         }
         int rc;
-        if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);   // pipelined
+        if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) {                                                // pipelined
+            if (l > 0 && a.Fprev.n_slabs > 1 && w.n_fsum > 0) {
+                // every CTA of a row block reads the whole input tile: sum the partial slabs of F_{l-1} once
+                rc = dgprf_launch_sum_slabs(a.Fprev, B, y.d_prev, wsf(ws, w.fsum), w.n_fsum, m->n_chains, st);
+                if (rc) return rc;
+                a.Fprev.ptr = wsf(ws, w.fsum); a.Fprev.cs = w.n_fsum; a.Fprev.ss = 0; a.Fprev.n_slabs = 1;
+            }
+            rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);
+        }
         else if (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a)) rc = dgprf_launch_fwd_tc(a, m->n_chains, st);
         else rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
         if (rc) return rc;
