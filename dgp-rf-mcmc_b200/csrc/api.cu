@@ -244,6 +244,38 @@ static SlabMat fpart_of(const dgprf_model* m, const WsLayout& w, void* ws, int l
 // ---- forward -----------------------------------------------------------------------------------
 static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X, int64_t x_cs, int B, int mode,
                         void* ws, float* F_out, cudaStream_t st) {
+    // ---- one launch prepares the TMA operands of every pipelined tensor-core layer (they depend on parameters only) ----
+    bool prepped = false;
+    {
+        PrepArgs p;
+        memset(&p, 0, sizeof(p));
+        p.n_layers = m->n_layers;
+        for (int l = 0; l < m->n_layers; ++l) {
+            const dgprf_layer& y = m->layer[l];
+            const LayerWs& s = w.L[l];
+            PrepLayer& q = p.L[l];
+            q.z = y.z; q.z_cs = y.z_cs;
+            q.log_inv_ls = m->h_base + y.off_log_inv_ls; q.mean = y.has_mean ? m->h_base + y.off_mean : nullptr; q.h_cs = m->h_cs;
+            q.W = m->w_base + y.off_W; q.w_cs = m->w_cs;
+            q.d = layer_d(y); q.M = y.M; q.F = layer_F(y); q.g = y.g; q.has_mean = y.has_mean;
+            q.NG = y.g <= 16 ? 16 : (y.g <= 32 ? 32 : 64);
+            q.Kp = (q.d + 31) & ~31;
+            if (s.tc2) {
+                q.wt = wsf(ws, s.wt); q.n_wt = ceil_div(q.F, 32) * ceil_div(q.NG, 32);
+                if (s.n_zt > 0) { q.zt = wsf(ws, s.zt); q.n_zt = ceil_div(q.M, 32) * 4; }
+                if (s.n_ot > 0) { q.ot = wsf(ws, s.ot); q.n_ot = ceil_div(q.M, 32) * (q.Kp / 32); }
+                prepped = true;
+            }
+            if (mode >= DGPRF_MODE_TRAIN && s.bwd2) {
+                q.wp = wsf(ws, s.wp); q.n_wp = ceil_div(q.F * 32, 256);
+                prepped = true;
+            }
+        }
+        if (prepped) {
+            const int rc = dgprf_launch_prep_layers(p, m->n_chains, st);
+            if (rc) return rc;
+        }
+    }
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
         FwdArgs a;
@@ -263,6 +295,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.phi_cs = w.L[l].n_phi;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
         if (w.L[l].tc2) {
+            a.prepped = prepped ? 1 : 0;
             a.wt = wsf(ws, w.L[l].wt);
             if (w.L[l].n_zt > 0) a.zt = wsf(ws, w.L[l].zt);
             if (w.L[l].n_at > 0) { a.at = wsf(ws, w.L[l].at); a.ot = wsf(ws, w.L[l].ot); }
@@ -365,6 +398,7 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         a.Tpart = hyper ? wsf(ws, w.L[l].tpart) : nullptr; a.t_cs = w.L[l].n_tpart;
         a.Rpart = hyper ? wsf(ws, w.L[l].rpart) : nullptr; a.r_cs = w.L[l].n_rpart;
         a.wp = w.L[l].bwd2 ? wsf(ws, w.L[l].wp) : nullptr;
+        a.prepped = w.L[l].bwd2 ? 1 : 0;          // forward_impl of this step wrote wp (k_prep_layers)
         int rc;
         if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc2_supported(a)) {
             if (a.dF.n_slabs > 1) {

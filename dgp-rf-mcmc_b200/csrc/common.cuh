@@ -93,6 +93,7 @@ struct FwdArgs {
     float* Fpart;    int64_t fpart_cs;   // [CS][B][g]
     float* zt; int64_t zt_cs; float* wt; // pipelined TC forward: prepped z^T hi/lo [2][M][128] and W^T [NG][F] (workspace)
     float* at; float* ot;                // ... WIDE variant: input hi/lo [2][B][Kp] and Omega^T hi/lo [2][M][Kp]
+    int32_t prepped;                     // zt / ot / wt were already written by k_prep_layers for this step
 };
 
 struct BwdArgs {
@@ -107,6 +108,7 @@ struct BwdArgs {
     float* Tpart;     int64_t t_cs;           // [CS][B][d]       raw T = dP z^T     (hyper)
     float* Rpart;     int64_t r_cs;           // [CS][B]          R = rowsum(dP)     (hyper | mean)
     float* wp;                                // pipelined TC backward: zero-padded W rows [F][32] (workspace)
+    int32_t prepped;                          // wp was already written by k_prep_layers for this step
 };
 
 // ---- device helpers ----------------------------------------------------------------------

@@ -570,9 +570,11 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
         int blocks = ceil_div(a.B, 8);
         if (blocks > 148 * 16) blocks = 148 * 16;
         k_prep_wide_a<<<dim3(blocks, n_chains), 256, 0, st>>>(a, Kp, a.at);
-        k_prep_wide_o<<<dim3(ceil_div(a.M, 32), Kp / 32, n_chains), 256, 0, st>>>(a, Kp, a.ot);
-        const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
-        k_prep_tc2<<<dim3(n_wt_tiles, n_chains), 256, 0, st>>>(a.z, a.z_cs, a.d, a.M, nullptr, 0, a.W, a.w_cs, a.F, a.g, NG, a.wt, (int64_t)NG * a.F);
+        if (!a.prepped) {
+            k_prep_wide_o<<<dim3(ceil_div(a.M, 32), Kp / 32, n_chains), 256, 0, st>>>(a, Kp, a.ot);
+            const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
+            k_prep_tc2<<<dim3(n_wt_tiles, n_chains), 256, 0, st>>>(a.z, a.z_cs, a.d, a.M, nullptr, 0, a.W, a.w_cs, a.F, a.g, NG, a.wt, (int64_t)NG * a.F);
+        }
         DGPRF_CHECK_CUDA(cudaGetLastError());
     }
     CUtensorMap mc, ms, mo, mw, ma;
@@ -610,7 +612,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
         configured = true;
     }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
-    {
+    if (!a.prepped) {
         const int n_zt_tiles = ceil_div(a.M, 32) * 4;
         const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
         ProfScope _ps("k_prep_tc2", st);

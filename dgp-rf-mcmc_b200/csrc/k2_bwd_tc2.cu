@@ -438,7 +438,7 @@ int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
         DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k2_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
         configured = true;
     }
-    {
+    if (!a.prepped) {
         ProfScope _ps("k_prep_bwd_tc2", st);
         k_prep_bwd_tc2<<<dim3(ceil_div(a.F * B2_NG, 256), n_chains), 256, 0, st>>>(a.W, a.w_cs, a.F, a.g, a.wp);
         DGPRF_CHECK_CUDA(cudaGetLastError());

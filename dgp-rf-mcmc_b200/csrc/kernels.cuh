@@ -41,6 +41,17 @@ struct HypArgs {
 };
 int dgprf_hyper_row_blocks(int B);
 
+// all-layer operand prep of the pipelined tensor-core kernels (k_prep_layers.cu)
+struct PrepLayer {
+    const float* z; int64_t z_cs; const float* log_inv_ls; const float* mean; int64_t h_cs;
+    const float* W; int64_t w_cs;
+    int32_t d, M, F, g, NG, Kp, has_mean;
+    float* zt; float* ot; float* wt; float* wp;          // outputs (the ones whose task count is non-zero)
+    int32_t n_zt, n_ot, n_wt, n_wp;                       // task (block) counts
+};
+struct PrepArgs { int32_t n_layers; PrepLayer L[DGPRF_MAX_LAYERS]; };
+int dgprf_launch_prep_layers(const PrepArgs& a, int n_chains, cudaStream_t st);
+
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_fwd_tc_supported(const FwdArgs& a);
 bool dgprf_fwd_tc2_supported(const FwdArgs& a);
