@@ -124,18 +124,23 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
         LayerWs& s = w->L[l];
-        s.CS = col_splits(y.M);
-        s.CSf = s.CS;
+        const int cs0 = col_splits(y.M);
+        s.CS = cs0;
+        s.CSf = cs0;
         s.tc_cols = 0;
         if (m->precision == DGPRF_PREC_TF32 && (y.M % 4) == 0 && y.g <= 64) {
             s.tc_cols = dgprf_tc_tile_cols(B, y.M, m->n_chains);
             const int t = ceil_div(y.M, s.tc_cols);
-            s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : s.CS;
+            s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : cs0;
             const int c2 = dgprf_fwd_tc2_col_splits(s.tc_cols, B, layer_d(y), y.M, y.g, m->n_chains);
             if (c2 > 0) { s.tc2 = 1; s.CSf = c2; }
         }
         s.n_fpart = (int64_t)s.CSf * B * y.g;
         s.fpart = take(s.n_fpart);
+        if (mode >= DGPRF_MODE_TRAIN && m->precision == DGPRF_PREC_TF32) {     // pipelined TC backward: its own column splits
+            const int pc = dgprf_bwd_tc2_pick_cs(B, y.M, y.g, layer_d(y), y.d_prev, w->RS, m->n_chains, mode == DGPRF_MODE_HYPER);
+            if (pc > 0) { s.bwd2 = 1; s.CS = pc; }
+        }
         if (mode >= DGPRF_MODE_TRAIN) {
             s.n_phi = (int64_t)B * layer_F(y);
             s.phi = take(s.n_phi);
@@ -145,9 +150,7 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
             s.n_tpart = (int64_t)s.CS * B * layer_d(y); s.tpart = take(s.n_tpart);
             s.n_rpart = (int64_t)s.CS * B;              s.rpart = take(s.n_rpart);
         }
-        if (mode >= DGPRF_MODE_TRAIN && m->precision == DGPRF_PREC_TF32 &&
-            dgprf_bwd_tc2_shape_ok(y.M, y.g, layer_d(y), y.d_prev, s.CS, mode == DGPRF_MODE_HYPER)) {
-            s.bwd2 = 1;
+        if (s.bwd2) {
             s.n_wp = dgprf_bwd_tc2_wp_floats(layer_F(y));
             s.wp = take(s.n_wp);
         }

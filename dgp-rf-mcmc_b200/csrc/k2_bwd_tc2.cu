@@ -427,6 +427,25 @@ bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper) 
 }
 int64_t dgprf_bwd_tc2_wp_floats(int F) { return (int64_t)F * B2_NG; }
 
+// Column splits for the pipelined backward (0: shape not supported).  A CTA (row split, column split, chain) pays a fixed
+// set-up (TMEM allocation, barrier init, first dF tile, pipeline fill; about three tile times) and then walks
+// ceil(n_ct / CS) x ceil(n_rt / RS) tiles, so with few row tiles per chain a small CS (more tiles per CTA, fewer CTAs)
+// beats the maximal split: pick the CS with the smallest  waves x (3 + tiles per CTA).
+int dgprf_bwd_tc2_pick_cs(int B, int M, int g, int d, int d_prev, int RS, int n_chains, int hyper) {
+    const int n_ct = ceil_div(M, B2_BN), n_rt = ceil_div(B, B2_BM);
+    const int rs_act = RS < n_rt ? RS : n_rt;
+    const int n_rloc = ceil_div(n_rt, rs_act);
+    int best = 0;
+    int64_t best_cost = 0;
+    for (int cs = 1; cs <= kMaxCS && cs <= n_ct; ++cs) {
+        if (!dgprf_bwd_tc2_shape_ok(M, g, d, d_prev, cs, hyper)) continue;
+        const int64_t ctas = (int64_t)rs_act * cs * n_chains;
+        const int64_t cost = ceil_div(ctas, (int64_t)148) * (3 + (int64_t)ceil_div(n_ct, cs) * n_rloc);
+        if (best == 0 || cost < best_cost || (cost == best_cost && cs > best)) { best = cs; best_cost = cost; }
+    }
+    return best;
+}
+
 bool dgprf_bwd_tc2_supported(const BwdArgs& a) {
     return a.wp != nullptr && (a.phi_cs % 4) == 0 && dgprf_bwd_tc2_shape_ok(a.M, a.g, a.d, a.d_prev, a.CS, a.hyper);
 }

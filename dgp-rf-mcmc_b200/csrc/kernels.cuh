@@ -65,6 +65,7 @@ int dgprf_tc_tile_cols(int B, int M, int n_chains);
 int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper);
 int64_t dgprf_bwd_tc2_wp_floats(int F);
+int dgprf_bwd_tc2_pick_cs(int B, int M, int g, int d, int d_prev, int RS, int n_chains, int hyper);
 bool dgprf_bwd_tc2_supported(const BwdArgs& a);
 int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_bwd_tc_supported(const BwdArgs& a);
