@@ -15,13 +15,14 @@
 // n_gp <= 32.  W-only mode: d_prev <= 64.  Hyper mode (stochastic-EM / full-Bayes gradients): T is formed for ALL input
 // columns (width <= 128, two passes of 64 z rows through the same z tile), and the raw T and R = rowsum(dP) are written as
 // the partial slabs k_hyper_reduce consumes.  Other shapes stay on k2_bwd_tc.cu / the SIMT kernel.
+#include <stdio.h>
 #include <stdlib.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
 constexpr int B2_BM = 128, B2_BN = 64, B2_NG = 32;
 constexpr int B2_EPI_WARPS = 8;
-constexpr int B2_THREADS = (B2_EPI_WARPS + 1) * 32;     // 8 epilogue warps + the issuer warp
+constexpr int B2_THREADS = (B2_EPI_WARPS + 2) * 32;     // 8 epilogue warps + the MMA issuer warp + the TMA producer warp
 constexpr int B2_BLK = B2_BM * 128;            // bytes of a [128 x 32 tf32] block
 constexpr int B2_HDR = 2048;                   // R_s | s_s | m_s | mbarriers | TMEM slot
 constexpr int B2_MAX_LOC = 10;                 // resident gW tiles: 10 x 32 TMEM columns
@@ -33,9 +34,10 @@ __device__ __forceinline__ void mbar_arrive_b2(uint64_t* bar) {
 }
 }  // namespace tc
 
-// Roles: warps 0-7 = epilogue (dF staging, dP, dF_prev, gW write-out); warp 8 = issuer: one elected thread issues
-// every TMA load and every UMMA, so no epilogue warp ever stalls behind MMA issue.  The two sides talk through
-// mbarriers only:
+// Roles: warps 0-7 = epilogue (dF staging, dP, dF_prev, gW write-out); warp 8 = MMA issuer (one elected thread issues every
+// UMMA); warp 9 = TMA producer (one elected thread issues every load).  Two single-thread roles because each mbarrier
+// wait costs a few hundred cycles even when it is already complete: one thread doing all nine waits of a tile took ~4000
+// cycles per tile and bounded the kernel.  The sides talk through mbarriers only:
 //   issuer -> epilogue   barA  MMA-1(k) done (dPhi in D1)        barB  MMA-3(k) done (dP / z tiles free, T final at a
 //                        row end)                                 barC  MMA-2(k) done (Phi stage and dF tile consumed)
 //   epilogue -> issuer   e_read  every warp has copied its Phi rows of tile k to registers (stage may be refilled)
@@ -43,7 +45,7 @@ __device__ __forceinline__ void mbar_arrive_b2(uint64_t* bar) {
 //                        dp_full every warp has written dP(k)
 //                        df_full the dF tile of the next row tile is staged
 __global__ void __launch_bounds__(B2_THREADS, 1)
-k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
+k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
            const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_z) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -63,7 +65,8 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     uint64_t* d1_free = bars + 10;    // count 8
     uint64_t* e_read1 = bars + 11;    // count 8
     uint64_t* barZ = bars + 12;       // first z pass of MMA-3 done (hyper mode with more than 64 input columns)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* barC1 = bars + 13;      // barC of the odd tiles (one barrier per Phi stage, like e_read)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     uint8_t* sPhi = sm + B2_HDR;                     // 2 stages x 4 blocks: cos 0,1 | sin 2,3   (32-byte-atom swizzle)
     uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
     uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
@@ -73,6 +76,8 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chain = blockIdx.z, cs = blockIdx.y, rs = blockIdx.x;
+    // debug timeline (DGPRF_BWD_TIMELINE=1): clock stamps of CTA 0, first 16 tiles, 12 events per tile
+#define TLB(t, ev) do { if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) tl[(t) * 12 + (ev)] = clock64(); } while (0)
     const bool rbf = a.kind == DGPRF_KIND_RBF;
     const float arc_scale = 1.41421356237f * __expf(__ldg(a.log_amp + chain * a.h_cs)) * rsqrtf((float)a.M);
     const bool hyper = a.hyper != 0;
@@ -91,6 +96,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
         for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1);
         for (int i = 7; i < 12; ++i) tc::mbar_init(bars + i, B2_EPI_WARPS);
         tc::mbar_init(barZ, 1);
+        tc::mbar_init(barC1, 1);
         tc::mbar_fence_init();
     }
     if (tid < 64) {
@@ -109,14 +115,14 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_d1 = tmem_base, tm_d3 = tmem_base + 128, tm_d2 = tmem_base + (hyper ? 256 : 192);
 
+    // tile k of this CTA = (row tile k / n_loc, column tile k % n_loc)
     if (warp == B2_EPI_WARPS) {
-        // ============================================ ISSUER ============================================
+        // ============================================ MMA ISSUER ============================================
         if (T > 0 && tc::elect_one()) {
             constexpr uint32_t IDESC1 = tc::make_idesc_tf32(B2_BM, 2 * B2_BN);
             constexpr uint32_t IDESC2 = tc::make_idesc_tf32_mn(B2_BM, B2_NG);
             const uint32_t IDESC3a = tc::make_idesc_tf32(B2_BM, nq0 > 0 ? nq0 : 16);
             const uint32_t IDESC3b = tc::make_idesc_tf32(B2_BM, nq1 > 0 ? nq1 : 16);
-            const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
             const uint64_t d_dF = tc::make_desc_sw128(tc::smem_u32(sdF));
             const uint64_t d_W = tc::make_desc_sw128(tc::smem_u32(sW));
             const uint64_t d_dP = tc::make_desc_sw128(tc::smem_u32(sdP));
@@ -124,27 +130,6 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             const uint64_t d_dF2 = tc::make_desc_mn_b32(tc::smem_u32(sdF2), B2_BLK, 512);
             const uint64_t d_Phi = tc::make_desc_mn_b32(tc::smem_u32(sPhi), B2_BLK, 512);
             const int k1steps = (a.g + 7) / 8;
-            // tile k of this CTA = (row tile k / n_loc, column tile k % n_loc)
-            auto load_phi = [&](int k) {
-                const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
-                tc::mbar_expect_tx(phi_full + s, phi_bytes);
-                for (int b = 0; b < 2; ++b) {
-                    tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
-                    if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
-                }
-            };
-            auto load_w = [&](int k) {
-                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
-                tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
-                tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
-                if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
-            };
-            auto load_z = [&](int k, int pass) {                    // z rows [64 pass, 64 pass + nq0) of the column tile
-                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
-                tc::mbar_expect_tx(z_full, 2u * nq0 * 128);
-                for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 64 * pass, zc);
-            };
-            int zph = 0;                                            // z_full phases consumed
             // MMA-1: dPhi = dF W_tile^T -> D1 (straight-line issue; the unused k-steps are predicated off)
             auto mma1 = [&](int k) {
                 tc::mbar_wait(w_full, k & 1);
@@ -165,13 +150,9 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
 #pragma unroll
                 for (int k8 = 0; k8 < B2_BM / 8; ++k8)
                     tc::umma_tf32(dcol, dphi + 64 * k8, d_dF2 + 64 * k8, IDESC2, k8 != 0 ? 1u : (rl != 0 ? 1u : 0u));
-                tc::umma_commit(barC);
+                tc::umma_commit(s ? barC1 : barC);
             };
-
-            load_phi(0);
-            if (T > 1) load_phi(1);
-            load_w(0);
-            if (NQ > 0) load_z(0, 0);
+            int zph = 0;                                            // z_full phases consumed
             tc::mbar_wait(df_full, 0);
             mma1(0);
             int rows_done = 0;                                      // df_full phases consumed so far - 1
@@ -179,23 +160,15 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 const int il = k % n_loc;
                 const bool row_end = il == n_loc - 1;
                 mma2(k);
-                tc::mbar_wait(barA, k & 1);                         // MMA-1(k) done: the W tile is free
-                if (k + 1 < T) load_w(k + 1);
-                if (NQ > 0 && k > 0) {                              // MMA-3(k-1) done: the z tile is free
-                    tc::mbar_wait(barB, (k - 1) & 1);
-                    load_z(k, 0);
-                }
-                if (k + 2 < T) {                                    // refill stage k & 1 once MMA-2(k) and the epilogue's reads are done
-                    tc::mbar_wait((k & 1) ? e_read1 : e_read, (k >> 1) & 1);
-                    tc::mbar_wait(barC, k & 1);
-                    load_phi(k + 2);
-                }
+                TLB(k, 6);
                 // inside a row tile, MMA-1 of the next tile goes out as soon as the epilogue holds dPhi(k) in registers,
                 // i.e. under the epilogue's math / stores; at a row end it has to wait for the next dF tile
                 tc::mbar_wait(d1_free, k & 1);
                 tc::tc_fence_after();
                 if (!row_end && k + 1 < T) mma1(k + 1);
+                TLB(k, 9);
                 tc::mbar_wait(dp_full, k & 1);                      // dP(k) written
+                TLB(k, 10);
                 tc::tc_fence_after();
                 if (NQ > 0) {
                     tc::mbar_wait(z_full, zph++ & 1);
@@ -206,10 +179,8 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                         for (int k4 = 0; k4 < 4; ++k4)
                             tc::umma_tf32(tm_d3, d_dP + (uint32_t)((b * B2_BLK + 32 * k4) >> 4),
                                           d_Z + (uint32_t)((b * 64 * 128 + 32 * k4) >> 4), IDESC3a, (b | k4) != 0 ? 1u : (il != 0 ? 1u : 0u));
-                    if (nq1 > 0) {                                  // second pass: z rows 64.. through the same tile
+                    if (nq1 > 0) {                                  // second pass: z rows 64.. through the same tile (producer reloads it)
                         tc::umma_commit(barZ);
-                        tc::mbar_wait(barZ, k & 1);
-                        load_z(k, 1);
                         tc::mbar_wait(z_full, zph++ & 1);
                         tc::tc_fence_after();
 #pragma unroll
@@ -221,11 +192,62 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                     }
                 }
                 tc::umma_commit(barB);
+                TLB(k, 11);
                 if (row_end && k + 1 < T) {                         // the next row tile's dF must be staged first
                     ++rows_done;
                     tc::mbar_wait(df_full, rows_done & 1);
                     tc::tc_fence_after();
                     mma1(k + 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == B2_EPI_WARPS + 1) {
+        // ============================================ TMA PRODUCER ============================================
+        // Every wait below is on a barrier whose NEXT phase needs a load this thread issues after the wait, so none of
+        // them can run two phases ahead of it.
+        if (T > 0 && tc::elect_one()) {
+            const uint32_t phi_bytes = (rbf ? 4u : 2u) * B2_BLK;
+            auto load_phi = [&](int k) {
+                const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
+                tc::mbar_expect_tx(phi_full + s, phi_bytes);
+                for (int b = 0; b < 2; ++b) {
+                    tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+                    if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
+                }
+            };
+            auto load_w = [&](int k) {
+                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+                tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
+                tc::tma_load_3d(&map_wp, tc::smem_u32(sW), w_full, 0, c0, chain);
+                if (rbf) tc::tma_load_3d(&map_wp, tc::smem_u32(sW + B2_BN * 128), w_full, 0, a.M + c0, chain);
+            };
+            auto load_z = [&](int k, int pass) {                    // z rows [64 pass, 64 pass + nq0) of the column tile
+                const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
+                tc::mbar_expect_tx(z_full, 2u * nq0 * 128);
+                for (int b = 0; b < 2; ++b) tc::tma_load_3d(&map_z, tc::smem_u32(sZ + b * (64 * 128)), z_full, c0 + 32 * b, 64 * pass, zc);
+            };
+            load_phi(0);
+            if (T > 1) load_phi(1);
+            load_w(0);
+            if (NQ > 0) load_z(0, 0);
+            for (int k = 0; k < T; ++k) {
+                tc::mbar_wait(barA, k & 1);                         // MMA-1(k) done: the W tile is free
+                TLB(k, 7);
+                if (k + 1 < T) load_w(k + 1);
+                if (NQ > 0 && nq1 > 0) {                            // hyper mode, > 64 input columns: second z pass of tile k
+                    tc::mbar_wait(barZ, k & 1);
+                    load_z(k, 1);
+                }
+                if (k + 2 < T) {                                    // refill stage k & 1 once MMA-2(k) and the epilogue's reads are done
+                    tc::mbar_wait((k & 1) ? e_read1 : e_read, (k >> 1) & 1);
+                    tc::mbar_wait((k & 1) ? barC1 : barC, (k >> 1) & 1);
+                    load_phi(k + 2);
+                }
+                TLB(k, 8);
+                if (NQ > 0 && k + 1 < T) {                          // MMA-3(k) done: the z tile is free for tile k+1
+                    tc::mbar_wait(barB, k & 1);
+                    load_z(k + 1, 0);
                 }
             }
         }
@@ -275,6 +297,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             const int s = k & 1;
             const bool row_end = il == n_loc - 1;
             tc::mbar_wait(phi_full + s, (k >> 1) & 1);        // the TMA-written tile is read by every thread below
+            if (tid == 0) TLB(k, 0);
             // ---- the thread's Phi values go to registers first so the ring stage can be refilled right away.  One
             //      release barrier per stage: its next phase needs the stage's next TMA load, which the issuer only
             //      requests after consuming this phase, so it can never run two phases ahead of the issuer's wait ----
@@ -287,7 +310,9 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_b2(s ? e_read1 : e_read);
+            if (tid == 0) TLB(k, 1);
             tc::mbar_wait(barA, k & 1);                       // dPhi of tile k is in D1
+            if (tid == 0) TLB(k, 2);
             tc::tc_fence_after();
             // ---- dPhi of the thread's row x 32 columns -> registers, then D1 is free for MMA-1 of the next tile ----
             float dcv[32], dsv[32];
@@ -304,7 +329,9 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_b2(d1_free);
+            if (tid == 0) TLB(k, 3);
             if (k > 0) tc::mbar_wait(barB, (k - 1) & 1);      // MMA-3(k-1) done: the dP tile may be overwritten
+            if (tid == 0) TLB(k, 4);
             // ---- dP -> dP tile (A of MMA-3), row sums ----
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {                  // 16-byte chunk inside the 32-wide block
@@ -332,6 +359,7 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_b2(dp_full);
+            if (tid == 0) TLB(k, 5);
             if (row_end) {
                 // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
                 R_s[hh * B2_BM + r] = rsum;
@@ -367,12 +395,12 @@ k2_bwd_tc2(const BwdArgs a, const __grid_constant__ CUtensorMap map_cos, const _
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s and D3 are read: the next row tile may reuse them
                 if (k + 1 < T) {
                     // its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
-                    tc::mbar_wait(barC, k & 1);
+                    tc::mbar_wait((k & 1) ? barC1 : barC, (k >> 1) & 1);
                     stage_dF((rs + (rl + 1) * a.RS) * B2_BM);
                 }
             }
         }
-        if (T > 0) tc::mbar_wait(barC, (T - 1) & 1);           // the last MMA-2: every gW tile is final
+        if (T > 0) tc::mbar_wait(((T - 1) & 1) ? barC1 : barC, ((T - 1) >> 1) & 1);   // the last MMA-2: every gW tile is final
         tc::tc_fence_after();
         // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
         if (warp < 4) {
@@ -479,7 +507,23 @@ int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
         if (rc) return rc;
     }
     dim3 grid(a.RS, a.CS, n_chains);
-    { ProfScope _ps("k2_bwd_tc2", st); k2_bwd_tc2<<<grid, B2_THREADS, kB2Smem, st>>>(a, mc, ms, mw, mz); }
+    static long long* tl = nullptr;                       // debug timeline (DGPRF_BWD_TIMELINE=<call number>)
+    static int tl_calls = 0;
+    if (getenv("DGPRF_BWD_TIMELINE") && !tl) cudaMalloc(&tl, 16 * 12 * sizeof(long long));
+    if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
+    { ProfScope _ps("k2_bwd_tc2", st); k2_bwd_tc2<<<grid, B2_THREADS, kB2Smem, st>>>(a, getenv("DGPRF_BWD_PF") ? atoi(getenv("DGPRF_BWD_PF")) : 0, tl, mc, ms, mw, mz); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
+    if (tl && ++tl_calls == atoi(getenv("DGPRF_BWD_TIMELINE"))) {
+        long long h[16 * 12];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, tl, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        fprintf(stderr, "bwd2 timeline (cycles since the epilogue saw tile 0)\n tile | epi: phi-ready Phi->regs dPhi-ready D1->regs dP-free dP-stored | issuer: mma2-issued mma1-done loads-issued mma1(k+1)-issued dP-seen mma3-issued\n");
+        for (int t = 0; t < 16; ++t) {
+            fprintf(stderr, " %3d |", t);
+            for (int e = 0; e < 12; ++e) fprintf(stderr, " %7lld%s", h[t * 12 + e] ? h[t * 12 + e] - t0 : -1LL, e == 5 ? " |" : "");
+            fprintf(stderr, "\n");
+        }
+    }
     return DGPRF_OK;
 }
