@@ -303,10 +303,21 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             //      requests after consuming this phase, so it can never run two phases ahead of the issuer's wait ----
             const uint8_t* ph = sPhi + s * 4 * B2_BLK;
             float4 pcv[8], psv[8];
+            // In the 32-byte-atom layout the 16-byte chunk cc of row r sits at unit (cc/2) ^ (r & 3), half cc & 1: at a fixed
+            // cc the 32 rows of a warp only touch 4 of the 8 16-byte bank groups.  Rows with (r >> 2) & 1 read the two
+            // halves of each unit in the opposite order (then swap the registers back), which covers all 8 groups.
+            const int hsw = (r >> 2) & 1;
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
-                pcv[cc] = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc));
-                if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc));
+                pcv[cc] = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc ^ hsw));
+                if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc ^ hsw));
+            }
+            if (hsw) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float4 t = pcv[j]; pcv[j] = pcv[j + 1]; pcv[j + 1] = t;
+                    if (rbf) { const float4 u = psv[j]; psv[j] = psv[j + 1]; psv[j + 1] = u; }
+                }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_b2(s ? e_read1 : e_read);
