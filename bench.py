@@ -357,7 +357,18 @@ def run_ours(args, rank, world):
         w1.record(stream)
         torch.cuda.synchronize()
         hbm_write_gbs = 5.0 * (1 << 30) / (w0.elapsed_time(w1) * 1e-3) / 1e9
-        del wbuf
+        # read-only ceiling (a sum over the same 1 GiB): what the backward's saved-feature load is held against
+        rbuf = wbuf.view(torch.float32)
+        for _ in range(2):
+            rbuf.sum()
+        torch.cuda.synchronize()
+        w0.record(stream)
+        for _ in range(5):
+            rbuf.sum()
+        w1.record(stream)
+        torch.cuda.synchronize()
+        hbm_read_gbs = 5.0 * (1 << 30) / (w0.elapsed_time(w1) * 1e-3) / 1e9
+        del wbuf, rbuf
 
         def tc_entry(name, alg_flops, exe_flops, what, hbm_peak, hbm_peak_name):
             if name not in tper:
@@ -371,7 +382,8 @@ def run_ours(args, rank, world):
         tc_layer = {
             "workload": f"one [RF->GP] layer at configs[4] scale: B={tB}, d={td}, M={tM}, n_gp={tg}, RBF, tf32 mode",
             "tf32_peak_tflops": tf32_peak, "hbm_copy_peak_gbs": pk["hbm_gbs"], "hbm_write_only_gbs": hbm_write_gbs,
-            "peak_source": pk_src + " (copy, bf16); write-only measured live with a 1 GiB fill",
+            "hbm_read_only_gbs": hbm_read_gbs,
+            "peak_source": pk_src + " (copy, bf16); write-only / read-only measured live with a 1 GiB fill / sum",
             "traffic_ncu_bytes": {"fwd": 2.104e9 + 84.0e6, "bwd": 2.166e9 + 4.2e6, "algorithmic_phi_bytes": phi_bytes,
                                   "source": "ncu --set full, profiles/r01_ncu_full_summary.md section E"},
             "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * 128 * tM + tF * tg),
@@ -379,7 +391,7 @@ def run_ours(args, rank, world):
                             hbm_write_gbs, "write-only"),
             "bwd": tc_entry("k2_bwd_tc2", 4.0 * tB * tF * tg, 4.0 * tB * tF * 32,
                             "dPhi = dF.W^T, gW += Phi^T.dF (accumulators resident in TMEM); Phi loaded (TMA ring)",
-                            pk["hbm_gbs"], "copy"),
+                            hbm_read_gbs, "read-only"),
         }
         del te, tX, tY
         torch.cuda.empty_cache()
