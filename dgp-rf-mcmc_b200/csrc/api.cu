@@ -133,7 +133,7 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
             const int t = ceil_div(y.M, s.tc_cols);
             s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : cs0;
             const int c2 = dgprf_fwd_tc2_col_splits(s.tc_cols, B, layer_d(y), y.M, y.g, m->n_chains);
-            if (c2 > 0) { s.tc2 = 1; s.CSf = c2; }
+            if (c2 > 0) { s.tc2 = 1; s.CSf = c2; s.tc_cols = 64; }
         }
         s.n_fpart = (int64_t)s.CSf * B * y.g;
         s.fpart = take(s.n_fpart);

@@ -663,9 +663,12 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
 // number of column splits (CTAs per row block; each walks M/64/splits column tiles) or 0 when the layered v1
 // kernel should run instead: the per-CTA prologue and pipeline fill only pay off over >= 4 tiles per CTA.
 int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains) {
-    if (tile_cols != 64 || (M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
+    if ((M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
     const int n_ct = ceil_div(M, V2_BN);
     const int64_t rb = (int64_t)ceil_div(B, V2_BM) * n_chains;
+    // grids too small for the v1 kernel's 64-column tiles (tile_cols == 32) still take this kernel, one tile per CTA if
+    // need be (measured faster from about 4 tiles in total); below that the v1 kernel with 32-column tiles runs
+    if (tile_cols != 64 && (rb * n_ct < 4 || getenv("DGPRF_NO_TC2_SMALL") != nullptr)) return 0;
     int cs = (int)((4 * 148 + rb - 1) / rb);                   // >= 4 waves of CTAs when the problem allows
     if (cs > kMaxCS) cs = kMaxCS;
     if (cs > n_ct) cs = n_ct;
@@ -676,8 +679,9 @@ int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_ch
         if (getenv("DGPRF_NO_TC2_WIDE") != nullptr || (int64_t)B * ((d + 31) & ~31) * n_chains > ((int64_t)1 << 28)) return 0;
         return cs;
     }
-    while (cs > 1 && n_ct / cs < 4) --cs;
-    return n_ct / cs >= 4 ? cs : 0;
+    const int min_tiles = getenv("DGPRF_TC2_MIN_TILES") ? atoi(getenv("DGPRF_TC2_MIN_TILES")) : (tile_cols != 64 ? 1 : 4);
+    while (cs > 1 && n_ct / cs < min_tiles) --cs;
+    return n_ct / cs >= min_tiles ? cs : 0;
 }
 bool dgprf_fwd_tc2_supported(const FwdArgs& a) {
     return a.wt != nullptr && (a.d <= 128 ? a.zt != nullptr : (a.at != nullptr && a.ot != nullptr)) &&

@@ -97,11 +97,11 @@ def test_tc_saved_features_and_gradients(name):
     s0 = e.spec.layers[0]
     Bn = X.shape[0]
     ctas64 = ((Bn + 127) // 128) * min((s0.M + 63) // 64, 8)
-    CS = min((s0.M + 31) // 32, 16) if ctas64 < 120 else min((s0.M + 63) // 64, 8)   # dgprf_tc_tile_cols
-    if ctas64 >= 120:                                                                 # dgprf_fwd_tc2_col_splits
-        n_ct, rb = (s0.M + 63) // 64, (Bn + 127) // 128
+    CS = min((s0.M + 31) // 32, 16) if ctas64 < 120 else min((s0.M + 63) // 64, 8)   # dgprf_tc_tile_cols (v1 kernel)
+    n_ct, rb = (s0.M + 63) // 64, (Bn + 127) // 128                                    # dgprf_fwd_tc2_col_splits
+    if ctas64 >= 120 or rb * n_ct >= 4:
         c2 = max(1, min((4 * 148 + rb - 1) // rb, 8, n_ct))
-        if s0.d > 128:
+        if s0.d > 128 or ctas64 < 120:
             CS = c2
         else:
             while c2 > 1 and n_ct // c2 < 4:
