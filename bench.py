@@ -399,23 +399,26 @@ def run_ours(args, rank, world):
         # ---- 8 independent chains batched per launch (configs[3]'s pattern on this workload) ------------
         from dgprf.chains import ChainEnsemble
         CH = 8
-        ens = ChainEnsemble(CFG["D"], 1, CFG["L"], CFG["n_rf"], CFG["n_gp"], input_cat=True, n_chains=CH, seed=7,
-                            precision=args.precision)
-        for i in range(10):
-            ens.sgmcmc_update(X[:B], Y[:B], N, **kw)
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        d0.record(stream)
-        MC_STEPS = 300
-        for i in range(MC_STEPS):
-            lo = (i % nb) * B
-            ens.sgmcmc_update(X[lo:lo + B], Y[lo:lo + B], N, **kw)
-        d1.record(stream)
-        torch.cuda.synchronize()
-        mc_ms = d0.elapsed_time(d1) / MC_STEPS
-        multi_chain = {"chains_per_gpu": CH, "value": CH * 1e3 / mc_ms, "unit": "chain-iterations/s",
-                       "ms_per_step_all_chains": mc_ms, "note": "independent chains batched in every launch; per GPU"}
-        del ens
+
+        def chains_run(prec):
+            ens = ChainEnsemble(CFG["D"], 1, CFG["L"], CFG["n_rf"], CFG["n_gp"], input_cat=True, n_chains=CH, seed=7, precision=prec)
+            for i in range(10):
+                ens.sgmcmc_update(X[:B], Y[:B], N, **kw)
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            d0.record(stream)
+            MC_STEPS = 300
+            for i in range(MC_STEPS):
+                lo = (i % nb) * B
+                ens.sgmcmc_update(X[lo:lo + B], Y[lo:lo + B], N, **kw)
+            d1.record(stream)
+            torch.cuda.synchronize()
+            ms = d0.elapsed_time(d1) / MC_STEPS
+            del ens
+            return {"chains_per_gpu": CH, "precision": prec, "value": CH * 1e3 / ms, "unit": "chain-iterations/s",
+                    "ms_per_step_all_chains": ms, "note": "independent chains batched in every launch; per GPU"}
+        multi_chain = chains_run(args.precision)
+        multi_chain_tf32 = chains_run("tf32") if args.precision != "tf32" else multi_chain
 
         # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------
         cpu_its, cpu_done, cpu_dt, threads = cpu_reference_run(10 ** 9, 10, budget_s=15.0)
@@ -441,6 +444,7 @@ def run_ours(args, rank, world):
                                    "frac": k5_gbs / pk["hbm_gbs"], "ms": k5_ms, "bytes": 20.0 * Cn * n_big,
                                    "peak_source": pk_src},
             "multi_chain": multi_chain,
+            "multi_chain_tf32": multi_chain_tf32,
             "roofline_tc_layer": tc_layer,
             "cpu_baseline": {"value": cpu_its, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_done} minibatch steps of the same workload in {cpu_dt:.1f} s"},
