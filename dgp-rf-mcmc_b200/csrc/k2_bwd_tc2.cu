@@ -413,26 +413,35 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
         }
         if (T > 0) tc::mbar_wait(((T - 1) & 1) ? barC1 : barC, ((T - 1) >> 1) & 1);   // the last MMA-2: every gW tile is final
         tc::tc_fence_after();
-        // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile) ----
-        if (warp < 4) {
-            const int fl = 32 * warp + lane;                               // feature row inside [cos 64 | sin 64]
+        // ---- the CTA's gW tiles -> row-split slab rs (zeros if the CTA had no row tile).  A tile goes TMEM -> shared
+        //      memory (the dP tile is idle now) -> global, so that the slab is written with coalesced stores: the
+        //      [64 features x g] blocks of the cos and of the sin half are contiguous in W's layout ----
+        {
+            float* stg = reinterpret_cast<float*>(sdP);                    // [128][33]
+            const int fl = 32 * (warp & 3) + lane;                         // feature row inside [cos 64 | sin 64]
             for (int i = 0; i < n_loc; ++i) {
-                const int c0 = (cs + i * a.CS) * B2_BN;
-                const int col = c0 + (fl & (B2_BN - 1));
-                const bool live = col < a.M && (rbf || fl < B2_BN);
-                const int64_t frow = (fl >= B2_BN ? a.M : 0) + col;
-                float* dst = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss + frow * a.g;
+                if (warp < 4) {
 #pragma unroll
-                for (int c16 = 0; c16 < B2_NG / 16; ++c16) {
-                    float v[16];
-                    tc::tmem_ld16(tm_d2 + i * B2_NG + ((uint32_t)(32 * warp) << 16) + 16 * c16, v);
-                    tc::tmem_ld_wait();
-                    if (live) {
+                    for (int c16 = 0; c16 < B2_NG / 16; ++c16) {
+                        float v[16];
+                        tc::tmem_ld16(tm_d2 + i * B2_NG + ((uint32_t)(32 * warp) << 16) + 16 * c16, v);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (16 * c16 + j < a.g) dst[16 * c16 + j] = T > 0 ? v[j] : 0.f;
+                        for (int j = 0; j < 16; ++j) stg[fl * 33 + 16 * c16 + j] = T > 0 ? v[j] : 0.f;
                     }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int c0 = (cs + i * a.CS) * B2_BN;
+                const int ncol = min(B2_BN, a.M - c0);                     // live feature columns of this tile
+                float* base = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss;
+                for (int half = 0; half < (rbf ? 2 : 1); ++half) {
+                    float* dst = base + ((int64_t)(half ? a.M : 0) + c0) * a.g;
+                    for (int e = tid; e < ncol * a.g; e += ET) {
+                        const int f = e / a.g, j = e - f * a.g;
+                        dst[e] = stg[(half * B2_BN + f) * 33 + j];
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
