@@ -175,6 +175,13 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         if (hend > w->h_len) w->h_len = hend;
     }
     if (m->off_lik_log_var + 1 > w->h_len) w->h_len = m->off_lik_log_var + 1;
+    {   // when every layer takes the pipelined backward (128-row tiles), row splits beyond the last row tile would only be
+        // zero slabs for the update to add: cap them (the per-layer column splits above already assumed min(RS, row tiles))
+        bool all_bwd2 = mode >= DGPRF_MODE_TRAIN;
+        for (int l = 0; l < m->n_layers; ++l) all_bwd2 = all_bwd2 && w->L[l].bwd2;
+        const int n_rt128 = ceil_div(B, 128);
+        if (all_bwd2 && w->RS > n_rt128) w->RS = n_rt128;
+    }
     w->w_len = round_up(w->w_len, 4);
     w->h_len = round_up(w->h_len, 4);
     w->llsum = take(1);
