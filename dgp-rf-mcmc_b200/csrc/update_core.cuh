@@ -18,14 +18,15 @@ template <int LPV>
 __device__ __forceinline__ float4 slab_sum_lane(const float* __restrict__ grad, int64_t part_stride, int n_part, int sub, int64_t i) {
     if (LPV == 1 && n_part == 1) return __ldcg(reinterpret_cast<const float4*>(grad + i));     // dense gradient
     float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p0 = sub; p0 < n_part; p0 += 8 * LPV) {
-        float4 gp[8];
+    constexpr int NB = LPV == 8 ? 16 : 8;                 // loads in flight per lane (8 lanes x 16 covers 128 slabs in one batch)
+    for (int p0 = sub; p0 < n_part; p0 += NB * LPV) {
+        float4 gp[NB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < NB; ++u)
             gp[u] = (p0 + u * LPV) < n_part ? __ldcg(reinterpret_cast<const float4*>(grad + (int64_t)(p0 + u * LPV) * part_stride + i))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { gsum.x += gp[u].x; gsum.y += gp[u].y; gsum.z += gp[u].z; gsum.w += gp[u].w; }
+        for (int u = 0; u < NB; ++u) { gsum.x += gp[u].x; gsum.y += gp[u].y; gsum.z += gp[u].z; gsum.w += gp[u].w; }
     }
     return gsum;
 }
