@@ -12,10 +12,54 @@ __global__ void k_sum_slabs(SlabMat m, int B, int ncol, float* out, int64_t out_
         out[chain * out_cs + e] = slab_load(m, chain, e / ncol, (int)(e % ncol));
 }
 
+// dense rows (ld == ncol): a slab is one contiguous array, so no index arithmetic and 128-bit accesses when aligned;
+// slabs are added in slab order (the order of slab_load), four loads in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(256) k_sum_slabs_dense(const float* __restrict__ base, int64_t cs, int64_t ss, int n_slabs, int64_t n,
+                                                         float* __restrict__ out, int64_t out_cs) {
+    const T* p = reinterpret_cast<const T*>(base + blockIdx.y * cs);
+    T* o = reinterpret_cast<T*>(out + blockIdx.y * out_cs);
+    const int64_t sst = ss / (int64_t)(sizeof(T) / sizeof(float));
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        T acc = __ldg(p + e);
+        int sl = 1;
+        for (; sl + 3 < n_slabs; sl += 4) {
+            const T t0 = __ldg(p + sl * sst + e), t1 = __ldg(p + (sl + 1) * sst + e), t2 = __ldg(p + (sl + 2) * sst + e),
+                    t3 = __ldg(p + (sl + 3) * sst + e);
+            if constexpr (sizeof(T) == 16) {
+                acc.x += t0.x; acc.y += t0.y; acc.z += t0.z; acc.w += t0.w;
+                acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+                acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
+                acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
+            } else {
+                acc += t0; acc += t1; acc += t2; acc += t3;
+            }
+        }
+        for (; sl < n_slabs; ++sl) {
+            const T t = __ldg(p + sl * sst + e);
+            if constexpr (sizeof(T) == 16) { acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+            else acc += t;
+        }
+        o[e] = acc;
+    }
+}
+
 int dgprf_launch_sum_slabs(const SlabMat& m, int B, int ncol, float* out, int64_t out_cs, int n_chains, cudaStream_t st) {
-    int blocks = ceil_div((int64_t)B * ncol, 256);
-    if (blocks > 1184) blocks = 1184;
-    k_sum_slabs<<<dim3(blocks, n_chains), 256, 0, st>>>(m, B, ncol, out, out_cs);
+    const int64_t n = (int64_t)B * ncol;
+    ProfScope _ps("k_sum_slabs", st);
+    if (m.ld == ncol) {
+        const bool v4 = (n % 4) == 0 && (m.ss % 4) == 0 && (m.cs % 4) == 0 && (out_cs % 4) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(m.ptr) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+        const int64_t nv = v4 ? n / 4 : n;
+        int blocks = (int)((nv + 255) / 256);
+        if (blocks > 2368) blocks = 2368;
+        if (v4) k_sum_slabs_dense<float4><<<dim3(blocks, n_chains), 256, 0, st>>>(m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs);
+        else k_sum_slabs_dense<float><<<dim3(blocks, n_chains), 256, 0, st>>>(m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs);
+    } else {
+        int blocks = ceil_div(n, 256);
+        if (blocks > 1184) blocks = 1184;
+        k_sum_slabs<<<dim3(blocks, n_chains), 256, 0, st>>>(m, B, ncol, out, out_cs);
+    }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -54,8 +98,8 @@ int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_
     int blocks = ceil_div(n, 256);
     if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
-    k_grad_finalize<<<dim3(blocks, n_chains), 256, 0, st>>>(part, part_cs, part_ss, n_part, theta, theta_cs,
-                                                            inv_N, out, out_cs, n);
+    { ProfScope _ps("k_grad_finalize", st);
+      k_grad_finalize<<<dim3(blocks, n_chains), 256, 0, st>>>(part, part_cs, part_ss, n_part, theta, theta_cs, inv_N, out, out_cs, n); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
