@@ -1,5 +1,6 @@
-// K1 v2 (tensor-core, DGPRF_PREC_TF32): warp-specialised, pipelined fused [RF layer -> GP layer] forward for
-// large problems (input width <= 128).  Same arithmetic as k1_fwd_tc.cu; what changes is the execution model:
+// K1 v2 (tensor-core, DGPRF_PREC_TF32): warp-specialised, pipelined fused [RF layer -> GP layer] forward (any layer with at
+// least four 128 x 64 tiles; input width <= 128, or any width in the WIDE variant).  Same arithmetic as k1_fwd_tc.cu; what
+// changes is the execution model:
 //
 //   * the A operand of GEMM #1, (in * exp(log_inv_ls)) split into tf32 hi + lo, is written ONCE per CTA into
 //     TENSOR MEMORY (tcgen05.st) and consumed from there by every column tile (tcgen05.mma with A in TMEM),
@@ -17,8 +18,9 @@
 //     GEMM #1 becomes a classic K loop in SS mode: a TMA ring of k-blocks [A hi | A lo | Omega hi | Omega lo] where A is the
 //     raw layer input and Omega = exp(log_inv_ls) * z + mean (both split into tf32 hi/lo by prep kernels), so neither the
 //     per-row scaling nor the mean bias is needed in the kernel; epilogue, GEMM #2 and the Phi store are unchanged;
-//   * the streamed operands are pre-laid for TMA by a small prep kernel per launch: z^T split into tf32
-//     hi/lo, K-major, zero-padded to 128 K columns ([2][M][128]) and W^T rounded to tf32 ([NG][F]).
+//   * the streamed operands are pre-laid for TMA once per step for all layers (k_prep_layers.cu; the prep kernels in this
+//     file serve stand-alone launches): z^T split into tf32 hi/lo, K-major, zero-padded to 128 K columns ([2][M][128]) and
+//     W^T rounded to tf32 ([NG][F]); debug: DGPRF_TC2_TIMELINE=<call number> prints per-role clock stamps of one CTA.
 #include <stdio.h>
 #include <stdlib.h>
 #include "kernels.cuh"

@@ -14,7 +14,9 @@
 //     kernel because a TMA row stride must be a multiple of 16 bytes; z directly from the model's spectral draws).
 // n_gp <= 32.  W-only mode: d_prev <= 64.  Hyper mode (stochastic-EM / full-Bayes gradients): T is formed for ALL input
 // columns (width <= 128, two passes of 64 z rows through the same z tile), and the raw T and R = rowsum(dP) are written as
-// the partial slabs k_hyper_reduce consumes.  Other shapes stay on k2_bwd_tc.cu / the SIMT kernel.
+// the partial slabs the hyper reduction (k_hyper_partial / k_hyper_final) consumes.  Other shapes stay on k2_bwd_tc.cu / the
+// SIMT kernel.  Column splits come from a small cost model (dgprf_bwd_tc2_pick_cs); debug: DGPRF_BWD_TIMELINE=<call number>
+// prints per-role clock stamps of one CTA, DGPRF_BWD_PF=<n> adds TMA L2 prefetches n tiles ahead of the ring (no gain measured).
 #include <stdio.h>
 #include <stdlib.h>
 #include "kernels.cuh"
