@@ -58,7 +58,8 @@ int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, 
     const int rc = dgprf_build_segtable(segs, n_seg, a.n, &tab);
     if (rc) return rc;
     const int64_t n4 = a.n >> 2;
-    const int lpv = a.n_part > 16 ? 8 : 1;
+    // 8 lanes per vector only pay off when there are many slabs AND too few vectors to fill the GPU with one thread each
+    const int lpv = (a.n_part > 16 && n4 * n_chains < (int64_t)148 * 2048) ? 8 : 1;
     int blocks = ceil_div(n4 * lpv, 256);
     const int cap = 148 * 8;
     if (blocks > cap) blocks = cap;
