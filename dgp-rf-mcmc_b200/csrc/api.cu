@@ -312,7 +312,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         }
         int rc;
         if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) {                                                // pipelined
-            if (l > 0 && a.Fprev.n_slabs > 1 && w.n_fsum > 0) {
+            if (l > 0 && a.Fprev.n_slabs > 1 && w.n_fsum > 0 && a.d <= 128) {      // (the WIDE variant's input split sums the slabs itself)
                 // every CTA of a row block reads the whole input tile: sum the partial slabs of F_{l-1} once
                 rc = dgprf_launch_sum_slabs(a.Fprev, B, y.d_prev, wsf(ws, w.fsum), w.n_fsum, m->n_chains, st);
                 if (rc) return rc;
