@@ -63,3 +63,17 @@ def rel_err(got, ref):
     ref = ref.detach().double().cpu().reshape(-1)
     scale = max(float(ref.abs().max()), 1e-30)
     return float((got - ref).abs().max()) / scale
+
+
+def assert_close(got, ref, rtol=1e-4, atol_scale=1e-6, what=""):
+    """Element-wise form of the contract (BASELINE.json north_star rtol 1e-4; SURVEY 8c: atol = 1e-6 * max|ref|):
+    |got - ref| <= atol_scale * max|ref| + rtol * |ref| for EVERY element, so errors on small entries count."""
+    got = got.detach().double().cpu().reshape(-1)
+    ref = ref.detach().double().cpu().reshape(-1)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    atol = atol_scale * max(float(ref.abs().max()), 1e-30)
+    excess = (got - ref).abs() - (atol + rtol * ref.abs())
+    worst = int(excess.argmax())
+    assert float(excess[worst]) <= 0.0, (
+        f"{what}: element {worst}: got {float(got[worst]):.9g}, ref {float(ref[worst]):.9g}, "
+        f"|diff| {abs(float(got[worst] - ref[worst])):.3g} > atol {atol:.3g} + rtol*|ref| {rtol * abs(float(ref[worst])):.3g}")
