@@ -79,6 +79,7 @@ struct WsLayout {
     LayerWs L[DGPRF_MAX_LAYERS];
     int RS;        // row splits of the layered backward (gW slabs)
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
+    int K10;       // the row-fused step is the cluster-split tensor-pipe kernel (RSF = its row tiles), else K9
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
     size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, fsum, total;
     int64_t n_dfsum, n_hpart, n_fsum;
@@ -189,7 +190,9 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     if (mode >= DGPRF_MODE_TRAIN) {
         w->n_dflast = (int64_t)B * m->d_out;
         w->dflast = take(w->n_dflast);
-        w->RSF = dgprf_step_rows_eligible(m, B) ? dgprf_step_rows_groups(B) : 0;
+        const int k10_tiles = dgprf_step_cluster_tiles(m, B);
+        w->K10 = k10_tiles > 0 ? 1 : 0;
+        w->RSF = k10_tiles > 0 ? k10_tiles : (dgprf_step_rows_eligible(m, B) ? dgprf_step_rows_groups(B) : 0);
         w->n_gwpart = (int64_t)(w->RS > w->RSF ? w->RS : w->RSF) * w->w_len;
         w->gwpart = take(w->n_gwpart);
         w->n_llpart = w->RSF > 0 ? w->RSF : 1;
@@ -551,9 +554,9 @@ extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x
         if (rc) return rc;
         ua.n_seg = n_seg_w;
         bool fused = false;
-        rc = dgprf_launch_step_rows(m, X, x_cs, Y, y_cs, B, wsf(ws, w.gwpart), w.n_gwpart, w.w_len,
-                                    wsf(ws, w.llpart), w.n_llpart, &ua, segs_w, n_seg_w,
-                                    reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.gridbar), u_out, &fused, st);
+        rc = (w.K10 ? dgprf_launch_step_cluster : dgprf_launch_step_rows)(
+            m, X, x_cs, Y, y_cs, B, wsf(ws, w.gwpart), w.n_gwpart, w.w_len, wsf(ws, w.llpart), w.n_llpart, &ua, segs_w,
+            n_seg_w, reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.gridbar), u_out, &fused, st);
         if (rc) return rc;
         if (fused) return DGPRF_OK;
         if (u_out) {

@@ -1,0 +1,909 @@
+// K10: cluster-split sampling step on the tensor pipe (fp32-accurate 3xTF32 mma.sync), small minibatches.
+//
+// A thread-block CLUSTER of CL CTAs owns RT = 16 | 32 batch rows and carries them through every layer, forward,
+// likelihood seed and the whole reverse pass (as K9 does with one CTA per 8 rows).  The random-feature columns of a
+// layer are split over the CL CTAs of the cluster: CTA `rank` owns P columns [rank*cols, (rank+1)*cols) and the
+// matching rows of W, so every z / W element is fetched from L2 by exactly ONE CTA of a cluster (K9: every CTA
+// re-staged all of z and W -- 125 copies per step at BASELINE configs[1]; here 32).  The only quantities that
+// cross CTAs are the [RT, g] partial outputs F_l (forward) and T_l = dP z^T (backward): each CTA leaves its
+// partial in shared memory, one cluster barrier, and every CTA sums the CL partials over distributed shared memory
+// in rank order (deterministic, identical on all CTAs).
+//
+// All five GEMMs of a layer run as mma.sync.m16n8k8 tf32 with the 3xTF32 split (a = hi + lo, drop lo*lo: fp32
+// accuracy, models/dgp.py rtol 1e-4 contract) and are chained through REGISTERS: the accumulator fragment of
+// P = in.(s*z) goes through sincos / relu in place and is re-used as the A fragment of F += Phi.W (the K order of a
+// reduction is free, so accumulator column 2t / 2t+1 is K slot t / t+4); the same holds backwards for
+// dPhi = dF.W^T -> dP -> T += dP.z^T.  gW^T = dF^T.Phi reads the saved Phi tile (shared memory, written and read by
+// the same warp) as its B fragment.  Operands (z, W) go straight from L2 into B fragments: each element is used once
+// per CTA, so there is no shared-memory staging and no block-wide barrier inside a GEMM chain.
+//
+// Arithmetic as K1/K2/K9 (layers/rf_layers.py:36-45,82-91; layers/GP_weight_layers.py:13; models/dgp.py:161-216):
+//   fwd  P = (in*s) z + in.mean;  Phi = amp/sqrt(M)[cos P, sin P] | sqrt(2) amp/sqrt(M) relu(P);  F = Phi W
+//   bwd  dPhi = dF W^T;  gW = Phi^T dF;  dP;  T = dP z^T;  dF_prev = s*T + mean*rowsum(dP)
+// The SGHMC / SGLD update runs behind a grid barrier in the same launch when every CTA is co-resident.
+#include <stdio.h>
+#include <stdlib.h>
+#include "kernels.cuh"
+#include "update_core.cuh"
+
+namespace {
+
+constexpr int kT = 512;          // threads per CTA
+constexpr int kW = kT / 32;      // warps
+constexpr int kNJ = 4;           // most 8-wide tiles of a GP output / previous-layer width (g, d_prev + 1 <= 32)
+constexpr int kFS = 33;          // row stride of the fp32 [RT][<=32] matrix f_s
+
+struct ClLayer {
+    int32_t kind, d_prev, d_x, M, g, has_mean;
+    int32_t cols;                // P columns per CTA (multiple of 8)
+    int32_t ldp;                 // row stride of the saved Phi tile [RT][ldp]
+    int32_t phi_off;             // float offset of the tile in the phi region
+    const float* z; int64_t z_cs;
+    const float* log_inv_ls; const float* log_amp; const float* mean;   // + chain*h_cs
+    const float* W;                                                     // + chain*w_cs
+    int64_t off_W;                                                      // into a gradient slab
+};
+
+struct ClArgs {
+    int32_t n_layers, likelihood, B, d_in, d_out, CL, lda, dmax, ncs;
+    int64_t h_cs, w_cs;
+    const float* X; int64_t x_cs;
+    const float* Y; int64_t y_cs;
+    const float* lik_log_var;
+    float* gwpart; int64_t gw_cs, gw_ss;     // [C][n_tiles][w_len]
+    float* ll_part; int64_t ll_cs;           // [C][n_tiles]
+    float inv_B;
+    int32_t fuse_update, upd_lpv;
+    unsigned int* bar;                       // [2] {arrival count, generation} (zero-initialised workspace words)
+    float* u_out;                            // [C] sum_i ll_i (nullable; fused path only)
+    long long* timing;                       // debug phase stamps of CTA 0 (nullable)
+    UpdArgs upd;
+    ClLayer layer[DGPRF_MAX_LAYERS];
+};
+
+// x = hi + lo, both rounded to nearest tf32 (ties away): adding half an ulp (0x1000) to the bit pattern and dropping the
+// low 13 bits -- which the tensor core does by itself, so lo is only biased, not masked.  Four instructions;
+// cvt.rna.tf32.f32 is a four-instruction emulation with an Inf/NaN guard on sm_100a (nine per hi / lo split).  Rounding
+// (not truncation) matters: truncated lo terms all err towards zero and the bias adds up coherently over a K = 1024 sum.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+// D += A(16x8, row) * B(8x8, col), tf32 in, fp32 accumulate.  lane = 4*g + t:
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   b0 (k=t, n=g)  b1 (k=t+4, n=g);
+//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 3xTF32: (ah + al)(bh + bl) without the al*bl term, small terms first
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32(c, al, bh0, bh1);
+    mma_tf32(c, ah, bl0, bl1);
+    mma_tf32(c, ah, bh0, bh1);
+}
+// accumulator fragment (cols 2t, 2t+1) -> A fragment (K slots t, t+4), split hi / lo
+__device__ __forceinline__ void acc_to_a(const float (&v)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    split_tf32(v[0], ah[0], al[0]);
+    split_tf32(v[2], ah[1], al[1]);
+    split_tf32(v[1], ah[2], al[2]);
+    split_tf32(v[3], ah[3], al[3]);
+}
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer(const float* local, uint32_t rank) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// Same self-resetting grid barrier as K9 (cooperative launch: all CTAs co-resident; bounded spin).
+__device__ __forceinline__ void grid_barrier_cl(unsigned int* bar, unsigned int my_gen, unsigned int n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int old = atomicAdd(bar, 1u);
+        if (old == n_ctas - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == my_gen)
+                if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Cross-warp + cross-CTA reduction of a per-warp accumulator set acc[MT][kNJ][4] (rows of the cluster's row tile x
+// nt*8 columns): warp partials -> `red`, fixed-order sum over the warps -> this CTA's partial in `fx`, one cluster
+// barrier, fixed-order sum over the CL ranks -> f_s[r][c] (every CTA of the cluster holds the identical result).
+template <int MT>
+__device__ __forceinline__ void reduce_exchange(const float (&acc)[MT][kNJ][4], int nt, float* __restrict__ red, float* __restrict__ fx,
+                                                float* __restrict__ f_s, int ncs, int CL) {
+    constexpr int RT = 16 * MT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < kNJ; ++j)
+            if (j < nt) {
+                float* p = red + ((warp * RT + mt * 16 + g) * ncs + j * 8 + 2 * t);
+                *reinterpret_cast<float2*>(p) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+                *reinterpret_cast<float2*>(p + 8 * ncs) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+            }
+    __syncthreads();
+    const int nc = nt * 8;
+    for (int e = tid; e < RT * nc; e += kT) {
+        const int r = e / nc, c = e - r * nc;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) s += red[(w * RT + r) * ncs + c];
+        if (CL > 1) fx[r * ncs + c] = s;
+        else f_s[r * kFS + c] = s;
+    }
+    if (CL > 1) {
+        cluster_sync_all();
+        for (int e = tid; e < RT * nc; e += kT) {
+            const int r = e / nc, c = e - r * nc;
+            float pv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pv[k] = k < CL ? ld_peer(fx + r * ncs + c, (uint32_t)k) : 0.f;    // all in flight
+            float s = pv[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) s += pv[k];          // rank order (adding the zeros of absent ranks is exact)
+            f_s[r * kFS + c] = s;
+        }
+    }
+    __syncthreads();
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant__ ClArgs a, const __grid_constant__ SegTable tab) {
+    constexpr int RT = 16 * MT;
+    constexpr int LDT = RT + 4;                          // row stride of the transposed dF operand
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int CL = a.CL, L = a.n_layers;
+    const int rank = CL > 1 ? (int)cluster_rank() : 0;
+    const int tile = blockIdx.x / CL, chain = blockIdx.y;
+    const int row0 = tile * RT;
+    unsigned int my_gen = 0;
+    if (a.fuse_update && tid == 0) my_gen = *reinterpret_cast<volatile unsigned int*>(a.bar + 1);
+
+    float* x_s   = sm;                                   // [RT][d_in]
+    float* f_s   = x_s + ((RT * a.d_in + 3) & ~3);       // [RT][kFS]   F_l / dF_l / raw T_l (fp32)
+    float* bias  = f_s + ((RT * kFS + 3) & ~3);          // [RT]        in . mean (forward); per-row log-likelihood
+    float* s_all = bias + RT;                            // [L][dmax]   exp(log_inv_ls)
+    float* m_all = s_all + L * a.dmax;                   // [L][dmax]   mean
+    float* a_hi  = m_all + L * a.dmax;                   // [RT][lda]   A operand of GEMM #1 (in*s) / of dPhi (dF), tf32 hi
+    float* a_lo  = a_hi + RT * a.lda;                    //             ... lo
+    float* t_hi  = a_lo + RT * a.lda;                    // [32][LDT]   dF^T (A operand of gW^T = dF^T Phi), hi
+    float* t_lo  = t_hi + 32 * LDT;                      //             ... lo
+    float* red   = t_lo + 32 * LDT;                      // [kW][RT][ncs] per-warp partials
+    float* fx0   = red + kW * RT * a.ncs;                // [2][RT][ncs] this CTA's partial, read by the cluster (ping-pong)
+    float* phi_all = fx0 + 2 * RT * a.ncs;               // per layer [RT][ldp]
+
+    const float* X = a.X + chain * a.x_cs;
+    const float* Y = a.Y + chain * a.y_cs;
+    int xph = 0;                                         // exchange-buffer parity
+    int tsi = 0;
+#define K10_STAMP() do { if (a.timing && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.timing[tsi] = clock64(); ++tsi; } while (0)
+    K10_STAMP();
+
+    // ---- L2 warm-up: this CTA's slices of z and W of every layer (first touch after an L2 flush is an HBM round trip)
+    for (int l = 0; l < L; ++l) {
+        const ClLayer& y = a.layer[l];
+        const int d = y.d_prev + y.d_x;
+        const int c_lo = rank * y.cols, c_hi = min(y.M, c_lo + y.cols);
+        if (c_hi <= c_lo) continue;
+        const float* z = y.z + chain * y.z_cs;
+        const float* W = y.W + chain * a.w_cs;
+        const int lpr = (c_hi - c_lo + 31) >> 5;         // 128-byte lines per z row slice
+        for (int e = tid; e < d * lpr; e += kT) {
+            const int q = e / lpr, i = e - q * lpr;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(z + (int64_t)q * y.M + c_lo + 32 * i));
+        }
+        const int nblk = y.kind == DGPRF_KIND_RBF ? 2 : 1;
+        const int lw = ((c_hi - c_lo) * y.g + 31) >> 5;
+        for (int e = tid; e < nblk * lw; e += kT) {
+            const int b = e / lw, i = e - b * lw;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(W + ((int64_t)b * y.M + c_lo) * y.g + 32 * i));
+        }
+    }
+    for (int e = tid; e < RT * a.d_in; e += kT) {
+        const int r = e / a.d_in, q = e - r * a.d_in;
+        x_s[e] = (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
+    }
+    for (int e = tid; e < L * a.dmax; e += kT) {
+        const int l = e / a.dmax, q = e - l * a.dmax;
+        const ClLayer& y = a.layer[l];
+        const bool ok = q < y.d_prev + y.d_x;
+        s_all[e] = ok ? expf(__ldg(y.log_inv_ls + chain * a.h_cs + q)) : 0.f;
+        m_all[e] = (ok && y.has_mean) ? __ldg(y.mean + chain * a.h_cs + q) : 0.f;
+    }
+    __syncthreads();
+
+    // =========================== forward ===========================
+    for (int l = 0; l < L; ++l) {
+        const ClLayer& y = a.layer[l];
+        const int d = y.d_prev + y.d_x, M = y.M, G = y.g;
+        const bool rbf = y.kind == DGPRF_KIND_RBF;
+        const int Kp = (d + 7) & ~7;
+        const float* s_s = s_all + l * a.dmax;
+        const float* m_s = m_all + l * a.dmax;
+        // ---- A operand: (in * s) split hi / lo, K zero-padded to Kp;  in = [F_{l-1} (f_s), X (x_s)]
+        for (int e = tid; e < RT * Kp; e += kT) {
+            const int r = e / Kp, q = e - r * Kp;
+            float v = 0.f;
+            if (q < y.d_prev) v = f_s[r * kFS + q] * s_s[q];
+            else if (q < d) v = x_s[r * a.d_in + (q - y.d_prev)] * s_s[q];
+            uint32_t hi, lo;
+            split_tf32(v, hi, lo);
+            a_hi[r * a.lda + q] = __uint_as_float(hi);
+            a_lo[r * a.lda + q] = __uint_as_float(lo);
+        }
+        if (tid < RT) {
+            float b = 0.f;
+            if (y.has_mean) {
+                for (int q = 0; q < y.d_prev; ++q) b = fmaf(f_s[tid * kFS + q], m_s[q], b);
+                for (int q = y.d_prev; q < d; ++q) b = fmaf(x_s[tid * a.d_in + (q - y.d_prev)], m_s[q], b);
+            }
+            bias[tid] = b;
+        }
+        __syncthreads();
+        K10_STAMP();
+
+        const int c_lo = rank * y.cols, c_hi = min(M, c_lo + y.cols);
+        const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
+        const float* z = y.z + chain * y.z_cs;
+        const float* W = y.W + chain * a.w_cs;
+        const float scale = (rbf ? 1.f : 1.41421356237f) * __expf(__ldg(y.log_amp + chain * a.h_cs)) * rsqrtf((float)M);
+        float* phi = phi_all + y.phi_off;
+        const int NJ = (G + 7) >> 3;
+        const int nblk = rbf ? 2 : 1;
+        float facc[MT][kNJ][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < kNJ; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) facc[mt][j][i] = 0.f;
+
+        for (int ti = warp; ti < ntile; ti += kW) {
+            const int n0 = c_lo + ti * 8;                 // first P column of this tile
+            // W fragments of GEMM #2 for this tile (both blocks), requested before GEMM #1 so they land under it:
+            // K slot t <-> feature f0 = n0 + 2t, slot t+4 <-> f0 + 1;  n <-> output column j = 8 jt + g
+            // Out-of-range rows / columns are CLAMPED instead of predicated: a clamped W column only feeds output columns
+            // >= G (never read), a clamped feature row meets Phi = 0.
+            float wv[2][kNJ][2];
+            {
+                const int f0 = min(n0 + 2 * t, c_hi - 1), f1 = min(n0 + 2 * t + 1, c_hi - 1);
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) {
+                        wv[b][j][0] = wv[b][j][1] = 0.f;
+                        if (b < nblk && j < NJ) {
+                            const int jj = min(j * 8 + g, G - 1);
+                            wv[b][j][0] = __ldg(W + (b * M + f0) * G + jj);
+                            wv[b][j][1] = __ldg(W + (b * M + f1) * G + jj);
+                        }
+                    }
+            }
+            // ---- GEMM #1: P tile [RT x 8] = A [RT x Kp] . z[:, n0:n0+8]
+            float acc[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+            const int col = min(n0 + g, c_hi - 1);        // clamped column: its Phi is zeroed in the epilogue
+            for (int k0 = 0; k0 < Kp; k0 += 32) {
+                float bz[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                 // clamped row: the K padding of A is zero
+                    const int q = k0 + 8 * u + t;
+                    bz[u][0] = __ldg(z + min(q, d - 1) * M + col);
+                    bz[u][1] = __ldg(z + min(q + 4, d - 1) * M + col);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k0 + 8 * u;
+                    if (kk < Kp) {
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32(bz[u][0], bh0, bl0);
+                        split_tf32(bz[u][1], bh1, bl1);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const float* ph = a_hi + (mt * 16 + g) * a.lda + kk + t;
+                            const float* pl = a_lo + (mt * 16 + g) * a.lda + kk + t;
+                            uint32_t ah[4], al[4];
+                            ah[0] = __float_as_uint(ph[0]); ah[1] = __float_as_uint(ph[8 * a.lda]);
+                            ah[2] = __float_as_uint(ph[4]); ah[3] = __float_as_uint(ph[8 * a.lda + 4]);
+                            al[0] = __float_as_uint(pl[0]); al[1] = __float_as_uint(pl[8 * a.lda]);
+                            al[2] = __float_as_uint(pl[4]); al[3] = __float_as_uint(pl[8 * a.lda + 4]);
+                            mma_3x(acc[mt], ah, al, bh0, bh1, bl0, bl1);
+                        }
+                    }
+                }
+            }
+            // ---- epilogue in registers: Phi = scale [cos P, sin P] | scale relu(P); saved for the backward
+            const int lc = n0 - c_lo + 2 * t;
+            float v[MT][4], w[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = mt * 16 + g + (i >> 1) * 8;
+                    const bool ok = (n0 + 2 * t + (i & 1)) < c_hi;
+                    const float p = acc[mt][i] + bias[r];
+                    if (rbf) {
+                        float sn, cs;
+                        sincos_cw(p, &sn, &cs);
+                        v[mt][i] = ok ? scale * cs : 0.f;
+                        w[mt][i] = ok ? scale * sn : 0.f;
+                    } else {
+                        v[mt][i] = ok ? scale * fmaxf(p, 0.f) : 0.f;
+                        w[mt][i] = 0.f;
+                    }
+                }
+                float* pr = phi + (mt * 16 + g) * y.ldp + lc;
+                *reinterpret_cast<float2*>(pr) = make_float2(v[mt][0], v[mt][1]);
+                *reinterpret_cast<float2*>(pr + 8 * y.ldp) = make_float2(v[mt][2], v[mt][3]);
+                if (rbf) {
+                    *reinterpret_cast<float2*>(pr + y.cols) = make_float2(w[mt][0], w[mt][1]);
+                    *reinterpret_cast<float2*>(pr + 8 * y.ldp + y.cols) = make_float2(w[mt][2], w[mt][3]);
+                }
+            }
+            // ---- GEMM #2 partial: F[RT x G] += Phi tile . W rows (accumulator fragment re-used as the A fragment)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                if (b < nblk) {
+                    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (b == 0) acc_to_a(v[mt], ah[mt], al[mt]);
+                        else acc_to_a(w[mt], ah[mt], al[mt]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j)
+                        if (j < NJ) {
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(wv[b][j][0], bh0, bl0);
+                            split_tf32(wv[b][j][1], bh1, bl1);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) mma_3x(facc[mt][j], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+                        }
+                }
+        }
+        K10_STAMP();
+        reduce_exchange<MT>(facc, NJ, red, fx0 + xph * RT * a.ncs, f_s, a.ncs, CL);      // f_s = F_l
+        xph ^= 1;
+        K10_STAMP();
+    }
+
+    // =========================== likelihood seed ===========================
+    // f_s = F_{L-1}; dU/dF_{L-1} overwrites it in place (one thread per row)
+    if (tid < RT) {
+        const int r = tid;
+        const int64_t row = row0 + r;
+        float* fr = f_s + r * kFS;
+        float ll = 0.f;
+        const bool live = row < a.B;
+        if (a.likelihood == DGPRF_LIK_GAUSSIAN) {
+            const float llv = __ldg(a.lik_log_var + chain * a.h_cs);
+            const float inv_var = expf(-llv);
+            for (int j = 0; j < a.d_out; ++j) {
+                const float res = live ? __ldg(Y + row * a.d_out + j) - fr[j] : 0.f;
+                ll += live ? -0.5f * (DGPRF_LOG_2PI + llv + res * res * inv_var) : 0.f;
+                fr[j] = -(res * inv_var) * a.inv_B;
+            }
+        } else {
+            float mx = -INFINITY;
+            for (int j = 0; j < a.d_out; ++j) mx = fmaxf(mx, fr[j]);
+            float se = 0.f;
+            for (int j = 0; j < a.d_out; ++j) se += expf(fr[j] - mx);
+            const float lse = mx + logf(se);
+            const int label = live ? (int)__ldg(Y + row) : 0;
+            ll = live ? ((label >= 0 && label < a.d_out) ? fr[label] : NAN) - lse : 0.f;
+            for (int j = 0; j < a.d_out; ++j) {
+                const float pj = expf(fr[j] - lse);
+                fr[j] = live ? (pj - (j == label ? 1.f : 0.f)) * a.inv_B : 0.f;
+            }
+        }
+        if (RT == 16) ll += __shfl_xor_sync(0x0000ffffu, ll, 8);
+        else ll += __shfl_xor_sync(0xffffffffu, ll, 16), ll += __shfl_xor_sync(0xffffffffu, ll, 8);
+        ll += __shfl_xor_sync(RT == 16 ? 0x0000ffffu : 0xffffffffu, ll, 4);
+        ll += __shfl_xor_sync(RT == 16 ? 0x0000ffffu : 0xffffffffu, ll, 2);
+        ll += __shfl_xor_sync(RT == 16 ? 0x0000ffffu : 0xffffffffu, ll, 1);
+        if (tid == 0 && rank == 0) a.ll_part[chain * a.ll_cs + tile] = ll;
+    }
+    __syncthreads();
+    K10_STAMP();
+
+    // =========================== backward ===========================
+    for (int l = L - 1; l >= 0; --l) {
+        const ClLayer& y = a.layer[l];
+        const int M = y.M, G = y.g;
+        const bool rbf = y.kind == DGPRF_KIND_RBF;
+        const int NJ = (G + 7) >> 3, MJ = (G + 15) >> 4;
+        const int nblk = rbf ? 2 : 1;
+        // ---- dF_l operands.  Top layer: f_s is dU/dF from the likelihood; below: f_s holds the raw T (and rowsum R in
+        //      column g) of the layer above, dF_l = s*T + mean*R with s / mean of layer l+1
+        {
+            const bool raw = l < L - 1;
+            const float* s_u = s_all + (l + 1) * a.dmax;
+            const float* m_u = m_all + (l + 1) * a.dmax;
+            const bool mean_u = raw && a.layer[l + 1].has_mean;
+            for (int e = tid; e < RT * 32; e += kT) {
+                const int r = e >> 5, c = e & 31;
+                float v = 0.f;
+                if (c < G) {
+                    v = f_s[r * kFS + c];
+                    if (raw) {
+                        v *= s_u[c];
+                        if (mean_u) v = fmaf(m_u[c], f_s[r * kFS + G], v);
+                    }
+                }
+                uint32_t hi, lo;
+                split_tf32(v, hi, lo);
+                if (c < NJ * 8) {
+                    a_hi[r * a.lda + c] = __uint_as_float(hi);
+                    a_lo[r * a.lda + c] = __uint_as_float(lo);
+                }
+                if (c < MJ * 16) {
+                    t_hi[c * LDT + r] = __uint_as_float(hi);
+                    t_lo[c * LDT + r] = __uint_as_float(lo);
+                }
+            }
+        }
+        __syncthreads();
+        K10_STAMP();
+
+        const int c_lo = rank * y.cols, c_hi = min(M, c_lo + y.cols);
+        const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
+        const float* z = y.z + chain * y.z_cs;
+        const float* W = y.W + chain * a.w_cs;
+        const float* phi = phi_all + y.phi_off;
+        float* gw = a.gwpart + chain * a.gw_cs + (int64_t)tile * a.gw_ss + y.off_W;
+        const float arc_scale = 1.41421356237f * __expf(__ldg(y.log_amp + chain * a.h_cs)) * rsqrtf((float)M);
+        const int nq_cols = y.d_prev + (y.has_mean ? 1 : 0);      // T columns (+ the row-sum column)
+        const int NQ = l > 0 ? (nq_cols + 7) >> 3 : 0;
+        float tacc[MT][kNJ][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < kNJ; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tacc[mt][j][i] = 0.f;
+
+        for (int ti = warp; ti < ntile; ti += kW) {
+            const int n0 = c_lo + ti * 8;
+            const int lc = n0 - c_lo;
+            if (l > 0) {
+                // z fragments of the T GEMM, requested first: K slot t <-> column n0 + 2t, slot t+4 <-> n0 + 2t + 1; n <-> q
+                float zv[kNJ][2];
+#pragma unroll
+                for (int j = 0; j < kNJ; ++j) {
+                    const int q = j * 8 + g, c0 = n0 + 2 * t;
+                    float b0 = 0.f, b1 = 0.f;
+                    if (j < NQ) {                             // clamped row / column: dP is zero beyond c_hi, T columns >= d_prev are never read
+                        const float* zp = z + min(q, y.d_prev - 1) * M;
+                        b0 = __ldg(zp + min(c0, c_hi - 1));
+                        b1 = __ldg(zp + min(c0 + 1, c_hi - 1));
+                        if (q == y.d_prev && y.has_mean) b0 = b1 = 1.f;      // the row-sum column R
+                    }
+                    zv[j][0] = b0; zv[j][1] = b1;
+                }
+                // ---- dPhi = dF . W^T for the tile's features: n <-> feature fb + n0 + g, k <-> j
+                float dacc[2][MT][4];
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dacc[b][mt][i] = 0.f;
+                const int fcl = min(n0 + g, c_hi - 1);        // clamped feature row of W: its dP is zero (Phi = 0 there)
+#pragma unroll
+                for (int j = 0; j < kNJ; ++j)
+                    if (j < NJ) {
+                        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const float* ph = a_hi + (mt * 16 + g) * a.lda + j * 8 + t;
+                            const float* pl = a_lo + (mt * 16 + g) * a.lda + j * 8 + t;
+                            ah[mt][0] = __float_as_uint(ph[0]); ah[mt][1] = __float_as_uint(ph[8 * a.lda]);
+                            ah[mt][2] = __float_as_uint(ph[4]); ah[mt][3] = __float_as_uint(ph[8 * a.lda + 4]);
+                            al[mt][0] = __float_as_uint(pl[0]); al[mt][1] = __float_as_uint(pl[8 * a.lda]);
+                            al[mt][2] = __float_as_uint(pl[4]); al[mt][3] = __float_as_uint(pl[8 * a.lda + 4]);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            if (b < nblk) {
+                                const int j0 = j * 8 + t;     // clamped k: the K padding of the dF operand is zero
+                                const float* wp = W + (b * M + fcl) * G;
+                                const float w0 = __ldg(wp + min(j0, G - 1));
+                                const float w1 = __ldg(wp + min(j0 + 4, G - 1));
+                                uint32_t bh0, bl0, bh1, bl1;
+                                split_tf32(w0, bh0, bl0);
+                                split_tf32(w1, bh1, bl1);
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt) mma_3x(dacc[b][mt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+                            }
+                    }
+                // ---- dP from the saved features (same fragment layout), then T += dP . z^T
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const float* pr = phi + (mt * 16 + g) * y.ldp + lc + 2 * t;
+                    const float2 c01 = *reinterpret_cast<const float2*>(pr);
+                    const float2 c23 = *reinterpret_cast<const float2*>(pr + 8 * y.ldp);
+                    float dp[4];
+                    if (rbf) {
+                        const float2 s01 = *reinterpret_cast<const float2*>(pr + y.cols);
+                        const float2 s23 = *reinterpret_cast<const float2*>(pr + 8 * y.ldp + y.cols);
+                        dp[0] = c01.x * dacc[1][mt][0] - s01.x * dacc[0][mt][0];
+                        dp[1] = c01.y * dacc[1][mt][1] - s01.y * dacc[0][mt][1];
+                        dp[2] = c23.x * dacc[1][mt][2] - s23.x * dacc[0][mt][2];
+                        dp[3] = c23.y * dacc[1][mt][3] - s23.y * dacc[0][mt][3];
+                    } else {
+                        dp[0] = c01.x > 0.f ? dacc[0][mt][0] * arc_scale : 0.f;
+                        dp[1] = c01.y > 0.f ? dacc[0][mt][1] * arc_scale : 0.f;
+                        dp[2] = c23.x > 0.f ? dacc[0][mt][2] * arc_scale : 0.f;
+                        dp[3] = c23.y > 0.f ? dacc[0][mt][3] * arc_scale : 0.f;
+                    }
+                    uint32_t ah[4], al[4];
+                    acc_to_a(dp, ah, al);
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j)
+                        if (j < NQ) {
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(zv[j][0], bh0, bl0);
+                            split_tf32(zv[j][1], bh1, bl1);
+                            mma_3x(tacc[mt][j], ah, al, bh0, bh1, bl0, bl1);
+                        }
+                }
+            }
+            // ---- gW^T [G x 8 features] = dF^T [G x RT] . Phi tile [RT x 8]: A from t_hi / t_lo, B from the saved tile
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                if (b < nblk) {
+                    float gacc[2][4];
+#pragma unroll
+                    for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) gacc[mj][i] = 0.f;
+#pragma unroll
+                    for (int kr = 0; kr < RT / 8; ++kr) {
+                        const float* pb = phi + (kr * 8 + t) * y.ldp + b * y.cols + lc + g;
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32(pb[0], bh0, bl0);
+                        split_tf32(pb[4 * y.ldp], bh1, bl1);
+#pragma unroll
+                        for (int mj = 0; mj < 2; ++mj)
+                            if (mj < MJ) {
+                                const float* ph = t_hi + (mj * 16 + g) * LDT + kr * 8 + t;
+                                const float* pl = t_lo + (mj * 16 + g) * LDT + kr * 8 + t;
+                                uint32_t ah[4], al[4];
+                                ah[0] = __float_as_uint(ph[0]); ah[1] = __float_as_uint(ph[8 * LDT]);
+                                ah[2] = __float_as_uint(ph[4]); ah[3] = __float_as_uint(ph[8 * LDT + 4]);
+                                al[0] = __float_as_uint(pl[0]); al[1] = __float_as_uint(pl[8 * LDT]);
+                                al[2] = __float_as_uint(pl[4]); al[3] = __float_as_uint(pl[8 * LDT + 4]);
+                                mma_3x(gacc[mj], ah, al, bh0, bh1, bl0, bl1);
+                            }
+                    }
+#pragma unroll
+                    for (int mj = 0; mj < 2; ++mj)
+                        if (mj < MJ) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int j = mj * 16 + g + (i >> 1) * 8, c = n0 + 2 * t + (i & 1);
+                                if (j < G && c < c_hi) gw[((int64_t)b * M + c) * G + j] = gacc[mj][i];
+                            }
+                        }
+                }
+        }
+        K10_STAMP();
+        if (l == 0) break;
+        reduce_exchange<MT>(tacc, NQ, red, fx0 + xph * RT * a.ncs, f_s, a.ncs, CL);      // f_s = raw T_l (| R_l)
+        xph ^= 1;
+        K10_STAMP();
+    }
+
+    // =========================== fused update (cooperative launch only) ===========================
+    if (a.fuse_update) {
+        // Everything of the update that does not depend on the other CTAs' gradient slabs runs BEFORE the grid barrier:
+        // theta / momentum loads and the Philox draws of this CTA's first pass of vectors hide under the wait.
+        const int64_t n4 = a.upd.n >> 2;
+        const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;          // 128-bit vectors per CTA
+        const int64_t v0 = (int64_t)blockIdx.x * per, v1 = min(n4, v0 + per);
+        const float* grad = a.upd.grad + chain * a.upd.grad_cs;
+        const bool lpv8 = a.upd_lpv == 8;
+        const int sub = lpv8 ? (tid & 7) : 0;
+        const int64_t vf = v0 + (lpv8 ? (tid >> 3) : tid);             // this thread's vector of the first pass
+        float4 th0 = make_float4(0.f, 0.f, 0.f, 0.f), mo0 = th0, e0 = th0;
+        if (sub == 0 && vf < v1) {
+            th0 = *reinterpret_cast<const float4*>(a.upd.theta + chain * a.upd.cs + (vf << 2));
+            mo0 = *reinterpret_cast<const float4*>(a.upd.mom + chain * a.upd.cs + (vf << 2));
+            sgmcmc_draw_vec(a.upd, chain, vf, e0, mo0);
+        }
+        grid_barrier_cl(a.bar, my_gen, gridDim.x * gridDim.y);
+        K10_STAMP();
+        if (lpv8) {
+            for (int64_t vb = v0; vb < v1; vb += kT / 8) {
+                const int64_t v = vb + (tid >> 3);
+                float4 gr = make_float4(0.f, 0.f, 0.f, 0.f), th = th0, mo = mo0, e = e0;
+                if (vb != v0 && sub == 0 && v < v1) {
+                    th = *reinterpret_cast<const float4*>(a.upd.theta + chain * a.upd.cs + (v << 2));
+                    mo = *reinterpret_cast<const float4*>(a.upd.mom + chain * a.upd.cs + (v << 2));
+                    sgmcmc_draw_vec(a.upd, chain, v, e, mo);
+                }
+                if (v < v1) gr = slab_sum_lane<8>(grad, a.upd.part_stride, a.upd.n_part, sub, v << 2);
+                gr = shuffle_sum_lpv<8>(gr);
+                if (sub == 0 && v < v1) sgmcmc_apply_vec(a.upd, tab, chain, v, gr, th, mo, e);
+            }
+        } else {
+            for (int64_t v = vf; v < v1; v += kT) {
+                float4 th = th0, mo = mo0, e = e0;
+                if (v != vf) {
+                    th = *reinterpret_cast<const float4*>(a.upd.theta + chain * a.upd.cs + (v << 2));
+                    mo = *reinterpret_cast<const float4*>(a.upd.mom + chain * a.upd.cs + (v << 2));
+                    sgmcmc_draw_vec(a.upd, chain, v, e, mo);
+                }
+                const float4 gr = slab_sum_lane<1>(grad, a.upd.part_stride, a.upd.n_part, 0, v << 2);
+                sgmcmc_apply_vec(a.upd, tab, chain, v, gr, th, mo, e);
+            }
+        }
+        if (a.u_out != nullptr && blockIdx.x == 0 && tid < 32) {        // minibatch log-likelihood, fixed order
+            const int n_tiles = gridDim.x / CL;
+            float s = 0.f;
+            for (int i = tid; i < n_tiles; i += 32) s += __ldcg(a.ll_part + chain * a.ll_cs + i);
+            s = warp_sum(s);
+            if (tid == 0) a.u_out[chain] = s;
+        }
+        K10_STAMP();
+    } else if (CL > 1) {
+        cluster_sync_all();          // no CTA may exit while a peer can still read its exchange buffer
+    }
+#undef K10_STAMP
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+struct ClPlan { int MT, CL, n_tiles; size_t smem; };
+
+int layer_cols(int M, int CL) { return (int)round_up(ceil_div(M, CL), 8); }
+int layer_ldp(int kind, int cols) {
+    const int Fl = kind == DGPRF_KIND_RBF ? 2 * cols : cols;
+    return Fl + ((Fl % 16) == 0 ? 8 : 16);
+}
+
+size_t plan_smem(const dgprf_model* m, int MT, int CL, int* lda_out, int* dmax_out, int* ncs_out) {
+    const int RT = 16 * MT;
+    int64_t dmax = 1, kpmax = 32, ncs = 8, phis = 0;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        const int d = y.d_prev + y.d_x;
+        if (d > dmax) dmax = d;
+        if (round_up(d, 8) > kpmax) kpmax = round_up(d, 8);
+        const int nj = 8 * ceil_div(y.g, 8), nq = l > 0 ? 8 * ceil_div(y.d_prev + (y.has_mean ? 1 : 0), 8) : 0;
+        if (nj > ncs) ncs = nj;
+        if (nq > ncs) ncs = nq;
+        phis += (int64_t)RT * layer_ldp(y.kind, layer_cols(y.M, CL));
+    }
+    dmax = round_up(dmax, 4);
+    const int lda = (int)kpmax + 4;
+    if (lda_out) *lda_out = lda;
+    if (dmax_out) *dmax_out = (int)dmax;
+    if (ncs_out) *ncs_out = (int)ncs;
+    const int64_t fl = round_up((int64_t)RT * m->d_in, 4) + round_up((int64_t)RT * kFS, 4) + RT + 2 * dmax * m->n_layers +
+                       2 * (int64_t)RT * lda + 2 * 32 * (RT + 4) + (int64_t)kW * RT * ncs + 2 * (int64_t)RT * ncs + phis;
+    return sizeof(float) * (size_t)fl;
+}
+
+// Geometry from (B, M_l, g_l, d_l) only -- never from the chain count, so that chain c of a batch computes exactly
+// what a single-chain model computes (bit for bit).
+bool make_plan(const dgprf_model* m, int B, ClPlan* p) {
+    if (m->precision != DGPRF_PREC_FP32 || getenv("DGPRF_NO_K10")) return false;
+    int Mmax = 1;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        if (y.g > 32 || y.d_prev + (y.has_mean ? 1 : 0) > 32 || y.d_prev + y.d_x > 1024) return false;
+        if (y.M > Mmax) Mmax = y.M;
+    }
+    if (m->d_out > 32) return false;
+    const char* e_mt = getenv("DGPRF_K10_MT");
+    const char* e_cl = getenv("DGPRF_K10_CL");
+    static const int cap[9] = {0, 148, 148, 0, 128, 0, 0, 0, 112};     // co-resident CTAs per cluster size (1 CTA / SM)
+    long best_cost = -1;
+    ClPlan best = {0, 0, 0, 0};
+    for (int MT = 2; MT >= 1; --MT)
+        for (int CL = 1; CL <= 8; CL *= 2) {
+            if (e_mt && atoi(e_mt) != MT) continue;
+            if (e_cl && atoi(e_cl) != CL) continue;
+            const int n_tiles = ceil_div(B, 16 * MT);
+            if ((int64_t)n_tiles * CL > cap[CL] && !(e_mt && e_cl)) continue;
+            const size_t smem = plan_smem(m, MT, CL, nullptr, nullptr, nullptr);
+            if (smem > 227 * 1024) continue;
+            // critical path ~ tiles a warp walks per GEMM chain
+            const long per_warp = ceil_div(ceil_div(layer_cols(Mmax, CL), 8), kW);
+            // (x 16 MT rows each), the operand round trips of those tiles, and a charge per cluster exchange
+            const long cost = 16 * MT * per_warp + 4 * per_warp + (CL > 1 ? 2 + CL / 2 : 0);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best.MT = MT; best.CL = CL; best.n_tiles = n_tiles; best.smem = smem;
+            }
+        }
+    if (best_cost < 0) return false;
+    *p = best;
+    return true;
+}
+
+}  // namespace
+
+int dgprf_step_cluster_tiles(const dgprf_model* m, int B) {
+    ClPlan p;
+    return make_plan(m, B, &p) ? p.n_tiles : 0;
+}
+
+// the opt-in dynamic shared-memory limit of the kernel only ever grows (per device)
+template <int MT>
+static int ensure_smem(size_t smem) {
+    static size_t configured[16] = {0};
+    int dev = 0;
+    DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16 || smem > configured[dev]) {
+        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k10_step_cluster<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 16) configured[dev] = smem;
+    }
+    return DGPRF_OK;
+}
+
+template <int MT>
+static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
+    const int rc0 = ensure_smem<MT>(smem);
+    if (rc0) return rc0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (a.CL > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = a.CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (coop) {
+        at[na].id = cudaLaunchAttributeCooperative;
+        at[na].val.cooperative = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k10_step_cluster<MT>, a, tab);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        dgprf_set_error("k10_step_cluster launch failed: %s (grid %u x %u, cluster %d, smem %zu, cooperative %d)",
+                        cudaGetErrorString(e), grid.x, grid.y, a.CL, smem, (int)coop);
+        return DGPRF_ECUDA;
+    }
+    return DGPRF_OK;
+}
+
+static int g_dbg_calls = 0;
+static int dbg_calls_peek() { return g_dbg_calls; }
+
+template <int MT>
+static int max_coresident(int CL, size_t smem) {
+    if (ensure_smem<MT>(smem) != DGPRF_OK) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k10_step_cluster<MT>, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n * CL;
+}
+
+// Same contract as dgprf_launch_step_rows: upd != nullptr asks for the fused update, *fused reports whether it ran.
+int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B,
+                              float* gwpart, int64_t gw_cs, int64_t gw_ss, float* ll_part, int64_t ll_cs,
+                              const UpdArgs* upd, const dgprf_segment* segs, int n_seg, unsigned int* bar, float* u_out,
+                              bool* fused, cudaStream_t st) {
+    ClPlan p;
+    DGPRF_REQUIRE(make_plan(m, B, &p), "step_cluster: model not eligible");
+    ClArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_layers = m->n_layers; a.likelihood = m->likelihood; a.B = B; a.d_in = m->d_in; a.d_out = m->d_out; a.CL = p.CL;
+    a.h_cs = m->h_cs; a.w_cs = m->w_cs;
+    a.X = X; a.x_cs = x_cs; a.Y = Y; a.y_cs = y_cs;
+    a.lik_log_var = m->likelihood == DGPRF_LIK_GAUSSIAN ? m->h_base + m->off_lik_log_var : nullptr;
+    a.gwpart = gwpart; a.gw_cs = gw_cs; a.gw_ss = gw_ss; a.ll_part = ll_part; a.ll_cs = ll_cs;
+    a.inv_B = 1.f / (float)B;
+    int lda = 0, dmax = 0, ncs = 0;
+    const size_t smem = plan_smem(m, p.MT, p.CL, &lda, &dmax, &ncs);
+    a.lda = lda; a.dmax = dmax; a.ncs = ncs;
+    int64_t phis = 0;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const dgprf_layer& y = m->layer[l];
+        ClLayer& s = a.layer[l];
+        s.kind = y.kind; s.d_prev = y.d_prev; s.d_x = y.d_x; s.M = y.M; s.g = y.g; s.has_mean = y.has_mean;
+        s.cols = layer_cols(y.M, p.CL); s.ldp = layer_ldp(y.kind, s.cols);
+        s.phi_off = (int32_t)phis;
+        phis += (int64_t)16 * p.MT * s.ldp;
+        s.z = y.z; s.z_cs = y.z_cs;
+        s.log_inv_ls = m->h_base + y.off_log_inv_ls; s.log_amp = m->h_base + y.off_log_amp;
+        s.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
+        s.W = m->w_base + y.off_W; s.off_W = y.off_W;
+    }
+    dim3 grid(p.n_tiles * p.CL, m->n_chains);
+    SegTable tab;
+    memset(&tab, 0, sizeof(tab));
+    *fused = false;
+    if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE")) {
+        static int cached[16][3][9];                     // [device][MT][CL] -> co-resident CTAs + 1 (0: not yet queried) ...
+        static size_t cached_smem[16][3][9];             // ... for this shared-memory size
+        int dev = 0;
+        DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+        int cap = 0;
+        if (dev < 16 && cached[dev][p.MT][p.CL] > 0 && cached_smem[dev][p.MT][p.CL] == smem) cap = cached[dev][p.MT][p.CL] - 1;
+        else {
+            cap = p.MT == 2 ? max_coresident<2>(p.CL, smem) : max_coresident<1>(p.CL, smem);
+            if (dev < 16) { cached[dev][p.MT][p.CL] = cap + 1; cached_smem[dev][p.MT][p.CL] = smem; }
+        }
+        if (getenv("DGPRF_K10_TIMING") && dbg_calls_peek() == 0)
+            fprintf(stderr, "k10: MT %d CL %d grid %u x %u smem %zu co-resident cap %d\n", p.MT, p.CL, grid.x, grid.y, smem, cap);
+        if ((int64_t)grid.x * grid.y <= cap) {
+            const int rc = dgprf_build_segtable(segs, n_seg, upd->n, &tab);
+            if (rc) return rc;
+            a.fuse_update = 1; a.bar = bar; a.u_out = u_out; a.upd = *upd;
+            a.upd_lpv = dgprf_update_lpv(upd->n_part, upd->n >> 2, m->n_chains);
+            *fused = true;
+        }
+    }
+    static long long* dbg = nullptr;                     // DGPRF_K10_TIMING=1: print phase cycle counts (debug only)
+    int& dbg_calls = g_dbg_calls;
+    if (getenv("DGPRF_K10_TIMING") && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+    a.timing = dbg;
+    int rc;
+    {
+        ProfScope _ps("k10_step_cluster", st);
+        rc = p.MT == 2 ? launch_cl<2>(a, tab, grid, smem, a.fuse_update != 0, st) : launch_cl<1>(a, tab, grid, smem, a.fuse_update != 0, st);
+        if (rc != DGPRF_OK && a.fuse_update) {           // cooperative + cluster launch refused: run unfused, K5 follows
+            if (getenv("DGPRF_K10_TIMING")) fprintf(stderr, "k10: fused launch refused: %s\n", dgprf_last_error());
+            a.fuse_update = 0;
+            *fused = false;
+            rc = p.MT == 2 ? launch_cl<2>(a, tab, grid, smem, false, st) : launch_cl<1>(a, tab, grid, smem, false, st);
+        }
+    }
+    if (rc) return rc;
+    const char* e_at = getenv("DGPRF_K10_TIMING");
+    if (dbg && ++dbg_calls == (e_at && atoi(e_at) > 1 ? atoi(e_at) : 30)) {
+        long long h[64];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const int n = 1 + 3 * m->n_layers + 1 + 3 * m->n_layers - 1 + (a.fuse_update ? 2 : 0);
+        fprintf(stderr, "k10 (MT %d, CL %d, grid %u) phase cycles:", p.MT, p.CL, grid.x);
+        for (int i = 1; i < n; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "  total %lld\n", h[n - 1] - h[0]);
+    }
+    return DGPRF_OK;
+}

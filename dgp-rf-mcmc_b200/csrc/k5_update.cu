@@ -51,6 +51,11 @@ int dgprf_build_segtable(const dgprf_segment* segs, int n_seg, int64_t n, SegTab
     return DGPRF_OK;
 }
 
+// 8 lanes per vector only pay off when there are many slabs AND too few vectors to fill the GPU with one thread each
+int dgprf_update_lpv(int n_part, int64_t n4, int n_chains) {
+    return (n_part > 16 && n4 * n_chains < (int64_t)148 * 2048) ? 8 : 1;
+}
+
 int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, int n_chains, cudaStream_t st) {
     DGPRF_REQUIRE((a.n & 3) == 0 && (a.cs & 3) == 0 && (a.grad_cs & 3) == 0 && (a.part_stride & 3) == 0,
                   "flat buffers must be padded to multiples of 4 floats");
@@ -58,8 +63,7 @@ int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, 
     const int rc = dgprf_build_segtable(segs, n_seg, a.n, &tab);
     if (rc) return rc;
     const int64_t n4 = a.n >> 2;
-    // 8 lanes per vector only pay off when there are many slabs AND too few vectors to fill the GPU with one thread each
-    const int lpv = (a.n_part > 16 && n4 * n_chains < (int64_t)148 * 2048) ? 8 : 1;
+    const int lpv = dgprf_update_lpv(a.n_part, n4, n_chains);
     int blocks = ceil_div(n4 * lpv, 256);
     const int cap = 148 * 8;
     if (blocks > cap) blocks = cap;

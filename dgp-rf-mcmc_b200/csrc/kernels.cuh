@@ -87,4 +87,12 @@ int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, c
                            float* gwpart, int64_t gw_cs, int64_t gw_ss, float* ll_part, int64_t ll_cs,
                            const UpdArgs* upd, const dgprf_segment* segs, int n_seg, unsigned int* bar, float* u_out,
                            bool* fused, cudaStream_t st);
+// cluster-split tensor-pipe step (k10_step_cluster.cu): 0 tiles = not eligible
+int dgprf_step_cluster_tiles(const dgprf_model* m, int B);
+int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B,
+                              float* gwpart, int64_t gw_cs, int64_t gw_ss, float* ll_part, int64_t ll_cs,
+                              const UpdArgs* upd, const dgprf_segment* segs, int n_seg, unsigned int* bar, float* u_out,
+                              bool* fused, cudaStream_t st);
+// lanes per 128-bit vector of the slab-summing update (K5 and the fused updates pick the same summation order)
+int dgprf_update_lpv(int n_part, int64_t n4, int n_chains);
 int dgprf_launch_sum_rows(const float* in, int64_t in_cs, int n, float* out, int n_chains, cudaStream_t st);

@@ -40,10 +40,26 @@ __device__ __forceinline__ float4 shuffle_sum_lpv(float4 g) {
     return g;
 }
 
-// Update the four parameters at flat offset i = 4*i4 of `chain` given their summed data gradient g and the
-// current values th / m (loaded by the caller together with the gradient so all three are in flight at once).
-__device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTable& tab, int chain, int64_t i4, float4 g,
-                                                  float4 th, float4 m) {
+// The random inputs of the update of vector i4 (independent of the gradient, so a fused kernel can draw them while it
+// waits at its grid barrier): e = the injected / Philox noise (zero at T = 0), m = the resampled momentum if asked.
+__device__ __forceinline__ void sgmcmc_draw_vec(const UpdArgs& a, int chain, int64_t i4, float4& e, float4& m) {
+    const int64_t i = i4 << 2;
+    if (a.resample) {
+        if (a.mom_inject) m = __ldg(reinterpret_cast<const float4*>(a.mom_inject + chain * a.cs + i));
+        else m = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base + 1u);
+    }
+    e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.noise_scale != 0.f) {
+        if (a.eps_inject) e = __ldg(reinterpret_cast<const float4*>(a.eps_inject + chain * a.cs + i));
+        else e = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base);
+    }
+}
+
+// Update the four parameters at flat offset i = 4*i4 of `chain` given their summed data gradient g, the current
+// values th / m (loaded by the caller together with the gradient so all three are in flight at once; m already
+// resampled if asked) and the noise e of sgmcmc_draw_vec.
+__device__ __forceinline__ void sgmcmc_apply_vec(const UpdArgs& a, const SegTable& tab, int chain, int64_t i4, float4 g,
+                                                 float4 th, float4 m, float4 e) {
     const int64_t i = i4 << 2;
     float* theta = a.theta + chain * a.cs;
     float* mom = a.mom + chain * a.cs;
@@ -61,15 +77,6 @@ __device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTab
         g.x = fmaf(th.x, a.inv_N, g.x); g.y = fmaf(th.y, a.inv_N, g.y);
         g.z = fmaf(th.z, a.inv_N, g.z); g.w = fmaf(th.w, a.inv_N, g.w);
     }
-    if (a.resample) {
-        if (a.mom_inject) m = __ldg(reinterpret_cast<const float4*>(a.mom_inject + chain * a.cs + i));
-        else m = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base + 1u);
-    }
-    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.noise_scale != 0.f) {
-        if (a.eps_inject) e = __ldg(reinterpret_cast<const float4*>(a.eps_inject + chain * a.cs + i));
-        else e = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base);
-    }
     const float ns = a.noise_scale * sqrt_mass, hm = a.h * inv_mass;
     m.x = fmaf(ns, e.x, fmaf(a.beta, m.x, -a.hN * g.x));
     m.y = fmaf(ns, e.y, fmaf(a.beta, m.y, -a.hN * g.y));
@@ -84,6 +91,13 @@ __device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTab
     }
     *reinterpret_cast<float4*>(theta + i) = th;
     *reinterpret_cast<float4*>(mom + i) = m;
+}
+
+__device__ __forceinline__ void sgmcmc_update_vec(const UpdArgs& a, const SegTable& tab, int chain, int64_t i4, float4 g,
+                                                  float4 th, float4 m) {
+    float4 e;
+    sgmcmc_draw_vec(a, chain, i4, e, m);
+    sgmcmc_apply_vec(a, tab, chain, i4, g, th, m, e);
 }
 
 // Host: validate the caller's segment list and build the kernel-parameter table.
