@@ -16,6 +16,29 @@ void dgprf_set_error(const char* fmt, ...) {
 
 extern "C" const char* dgprf_last_error(void) { return g_err; }
 
+// ---- per-(kernel, device) shared-memory opt-in -------------------------------------------------
+#include <mutex>
+#include <vector>
+struct SmemRec { const void* k; int dev; size_t smem; };
+int dgprf_ensure_smem(const void* kernel, size_t smem) {
+    static std::mutex mu;
+    static std::vector<SmemRec> recs;
+    int dev = 0;
+    DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& r : recs)
+        if (r.k == kernel && r.dev == dev) {
+            if (smem > r.smem) {
+                DGPRF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                r.smem = smem;
+            }
+            return DGPRF_OK;
+        }
+    DGPRF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    recs.push_back({kernel, dev, smem});
+    return DGPRF_OK;
+}
+
 // ---- measurement hook ---------------------------------------------------------------------------
 #include <vector>
 #include <string>

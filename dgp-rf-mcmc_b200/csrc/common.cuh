@@ -34,6 +34,9 @@ struct ProfScope {
     ~ProfScope() { dgprf_prof_end(st); }
 };
 
+// Opt-in dynamic shared-memory limit of a kernel, remembered per (kernel, device) and only ever raised (api.cu).
+int dgprf_ensure_smem(const void* kernel, size_t smem);
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }
 

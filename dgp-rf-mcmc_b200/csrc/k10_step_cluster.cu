@@ -759,18 +759,8 @@ int dgprf_step_cluster_tiles(const dgprf_model* m, int B) {
     return make_plan(m, B, &p) ? p.n_tiles : 0;
 }
 
-// the opt-in dynamic shared-memory limit of the kernel only ever grows (per device)
 template <int MT>
-static int ensure_smem(size_t smem) {
-    static size_t configured[16] = {0};
-    int dev = 0;
-    DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev >= 16 || smem > configured[dev]) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k10_step_cluster<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev < 16) configured[dev] = smem;
-    }
-    return DGPRF_OK;
-}
+static int ensure_smem(size_t smem) { return dgprf_ensure_smem((const void*)k10_step_cluster<MT>, smem); }
 
 template <int MT>
 static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {

@@ -197,11 +197,7 @@ static size_t fwd_smem_bytes(int GP) {
 template <int GP>
 static int launch_fwd(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const size_t smem = fwd_smem_bytes(GP);
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_simt<GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_simt<GP>, (size_t)smem); if (rc_s) return rc_s; }
     dim3 grid(ceil_div(a.B, kTM), a.CS, n_chains);
     { ProfScope _ps("k1_fwd_simt", st); k1_fwd_simt<GP><<<grid, kThreads, smem, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());

@@ -292,11 +292,7 @@ static size_t tc_fwd_smem_bytes(int NG, int BN) {
 template <int NG, int BN>
 static int launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const size_t smem = tc_fwd_smem_bytes(NG, BN);
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc<NG, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc<NG, BN>, (size_t)smem); if (rc_s) return rc_s; }
     CUtensorMap mc, ms;
     memset(&mc, 0, sizeof(mc));
     memset(&ms, 0, sizeof(ms));

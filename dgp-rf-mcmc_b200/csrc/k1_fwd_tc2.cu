@@ -561,11 +561,7 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     int ns = 3;
     while (ns > 1 && tc2_wide_smem_bytes(NG, nsw, ns) > 232448) --ns;
     const size_t smem = tc2_wide_smem_bytes(NG, nsw, ns);
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc2<NG, true>, (size_t)232448); if (rc_s) return rc_s; }
     DGPRF_REQUIRE(a.at != nullptr && a.ot != nullptr && a.wt != nullptr, "wide pipelined forward needs the prepped operand buffers");
     {
         ProfScope _ps("k_prep_tc2_wide", st);
@@ -608,11 +604,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const int n_kb = (a.d + 31) / 32;
     const int ns1 = tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1;
     const size_t smem = tc2_smem_bytes(NG, n_kb, ns1);
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k1_fwd_tc2<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc2<NG, false>, (size_t)232448); if (rc_s) return rc_s; }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
     if (!a.prepped) {
         const int n_zt_tiles = ceil_div(a.M, 32) * 4;

@@ -259,11 +259,7 @@ static size_t bwd_smem_bytes(int GP, int d) {
 template <int GP>
 static int launch_bwd(const BwdArgs& a, int n_chains, cudaStream_t st) {
     const size_t smem = bwd_smem_bytes(GP, a.d);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k2_bwd_simt<GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k2_bwd_simt<GP>, (size_t)smem); if (rc_s) return rc_s; }
     dim3 grid(a.RS, a.CS, n_chains);
     { ProfScope _ps("k2_bwd_simt", st); k2_bwd_simt<GP><<<grid, kThreads, smem, st>>>(a); }
     DGPRF_CHECK_CUDA(cudaGetLastError());

@@ -293,11 +293,7 @@ static size_t tc_bwd_smem_bytes(int NG) {
 template <int NG>
 static int launch_bwd_tc(const BwdArgs& a, int n_chains, cudaStream_t st) {
     const size_t smem = tc_bwd_smem_bytes(NG);
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k2_bwd_tc<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k2_bwd_tc<NG>, (size_t)smem); if (rc_s) return rc_s; }
     CUtensorMap mc, ms;
     memset(&mc, 0, sizeof(mc));
     memset(&ms, 0, sizeof(ms));

@@ -502,11 +502,7 @@ bool dgprf_bwd_tc2_supported(const BwdArgs& a) {
 
 int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
     static_assert(kB2Smem <= 232448, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k2_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
-        configured = true;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k2_bwd_tc2, (size_t)kB2Smem); if (rc_s) return rc_s; }
     if (!a.prepped) {
         ProfScope _ps("k_prep_bwd_tc2", st);
         k_prep_bwd_tc2<<<dim3(ceil_div(a.F * B2_NG, 256), n_chains), 256, 0, st>>>(a.W, a.w_cs, a.F, a.g, a.wp);

@@ -701,24 +701,25 @@ int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, c
     }
     a.dmax = (int32_t)round_up(dmax, 4); a.Fmax = (int32_t)Fmax; a.bs_cap = step_rows_bs_cap(m); a.zr_cap = step_rows_zr_cap(m);
     const size_t smem = dgprf_step_rows_smem(m);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DGPRF_CHECK_CUDA(cudaFuncSetAttribute(k9_step_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_s = dgprf_ensure_smem((const void*)k9_step_rows, smem); if (rc_s) return rc_s; }
     dim3 grid(ceil_div(B, kSR), m->n_chains);
     SegTable tab;
     memset(&tab, 0, sizeof(tab));
     *fused = false;
     if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE")) {
-        static int max_coresident = -1;
-        if (max_coresident < 0) {
-            int dev = 0, sms = 0, per_sm = 0;
-            DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+        // co-resident CTAs for THIS shared-memory size on THIS device (a process-wide cache computed for the first
+        // model would let a later, larger model through to a cooperative launch that cannot fit)
+        static int cache_dev = -1, cache_val = 0;
+        static size_t cache_smem = 0;
+        int dev = 0;
+        DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev != cache_dev || smem != cache_smem) {
+            int sms = 0, per_sm = 0;
             DGPRF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             DGPRF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k9_step_rows, kST, smem));
-            max_coresident = sms * per_sm;
+            cache_dev = dev; cache_smem = smem; cache_val = sms * per_sm;
         }
+        const int max_coresident = cache_val;
         if ((int64_t)grid.x * grid.y <= max_coresident) {
             const int rc = dgprf_build_segtable(segs, n_seg, upd->n, &tab);
             if (rc) return rc;
@@ -736,7 +737,12 @@ int dgprf_launch_step_rows(const dgprf_model* m, const float* X, int64_t x_cs, c
         ProfScope _ps("k9_step_rows", st);
         if (a.fuse_update) {
             void* kargs[2] = {&a, &tab};
-            DGPRF_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)k9_step_rows, grid, dim3(kST), kargs, smem, st));
+            if (cudaLaunchCooperativeKernel((const void*)k9_step_rows, grid, dim3(kST), kargs, smem, st) != cudaSuccess) {
+                (void)cudaGetLastError();             // refused (e.g. the GPU is shared): run unfused, K5 follows
+                a.fuse_update = 0;
+                *fused = false;
+                k9_step_rows<<<grid, kST, smem, st>>>(a, tab);
+            }
         } else {
             k9_step_rows<<<grid, kST, smem, st>>>(a, tab);
         }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import os
 
+import collections
 import ctypes as C
 import math
 from dataclasses import dataclass, field
@@ -118,6 +119,8 @@ class Engine:
         self.z = z
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._staging: Dict = {}
+        self._inflight = collections.deque()     # host minibatches the GPU may still be reading: (event | None, tensors)
+        self._held = 0
         self._model = None
         self._scratch = torch.zeros(max(4, self.C), **f32)
         # segment tables: name -> (offset, length, mass, flags)
@@ -331,9 +334,23 @@ class Engine:
                   u_host: Optional[torch.Tensor] = None):
         """sgmcmc_update from a HOST minibatch (fp32 contiguous CPU tensors, ideally pinned): the H2D copies,
         the step and the optional D2H read of sum_i ll_i are enqueued by ONE C call; nothing synchronises.
-        Everything that does not change between steps is converted to ctypes once and cached."""
+        Everything that does not change between steps is converted to ctypes once and cached.
+
+        Lifetime contract (the reference's sgmcmc_update consumes its batch by value, models/dgp.py:184): PINNED
+        buffers are read by the GPU in place, after this call has returned.  The engine therefore keeps a reference to
+        X_host / Y_host / u_host until a CUDA event recorded after the step has completed, so a caller that drops its
+        batch right away (a DataLoader(pin_memory=True) loop) cannot have the block recycled under the kernel.
+        What the caller must not do is WRITE into the same pinned tensors before the step has run (synchronise, or
+        use a fresh / pageable tensor per step -- pageable batches are staged by value by the driver)."""
         B, dx = X_host.shape
+        if self.spec.likelihood == "softmax" and Y_host.shape[1] != 1:
+            Y_host = Y_host[:, :1].contiguous()         # labels live in column 0 (likelihoods/softmax.py:14), as _xy does
+            if X_host.is_pinned():
+                Y_host = Y_host.pin_memory()
         yc = Y_host.shape[1]
+        assert yc == (self.spec.d_out if self.spec.likelihood == "gaussian" else 1), \
+            f"Y has width {yc}, the likelihood expects {self.spec.d_out if self.spec.likelihood == 'gaussian' else 1}"
+        assert Y_host.shape[0] == B and dx == self.spec.d_in, "X / Y shape does not match the model / batch"
         key = (B, yc, full_bayesian)
         st = self._staging.get(key)
         if st is None:
@@ -370,6 +387,30 @@ class Engine:
                 torch.cuda.current_stream().cuda_stream)
         if rc:
             _ffi.check(rc)
+        if zc:
+            self._hold(X_host, Y_host, u_host)
+
+    def _hold(self, *tensors):
+        """Keep zero-copy host buffers alive until the GPU is done with them: every 8th step records an event; entries
+        up to the newest completed event are released (at most 64 steps are ever outstanding)."""
+        self._held += 1
+        ev = None
+        if (self._held & 7) == 0:
+            ev = torch.cuda.Event()
+            ev.record()
+        q = self._inflight
+        q.append((ev, tensors))
+        done = -1
+        for i, (e, _) in enumerate(q):
+            if e is not None:
+                if len(q) - i > 64:
+                    e.synchronize()
+                if e.query():
+                    done = i
+                else:
+                    break
+        for _ in range(done + 1):
+            q.popleft()
 
     def log_prior(self, t: torch.Tensor) -> torch.Tensor:
         """sum log N(t; 0, 1) over a contiguous tensor -> scalar tensor (models/dgp.py:129-136)."""

@@ -11,6 +11,7 @@ Extensions (keyword-only, default = reference behaviour): ``eps`` / ``resample``
 inject the N(0,1) draws by parameter NAME for parity tests; ``grad_U`` exposes the gradients
 that the reference obtains from tf.GradientTape.
 """
+import contextlib
 import math
 import os
 
@@ -208,9 +209,33 @@ class DGP_RF:
             return out(self._log_prior_of(vs)) if vs else 0.
         raise NotImplementedError
 
+    @contextlib.contextmanager
+    def _z_for_call(self):
+        """random_fixed=False (layers/rf_layers.py:39-41, 85-87): the reference draws a fresh z inside EVERY forward, also
+        the one under the GradientTape of U / sgmcmc_update / precond_update.  The fused kernels read z from the engine
+        buffers, so one fresh draw is put there for the duration of one potential / gradient / step evaluation (forward
+        and backward of a step see the same draw, as under one tape) and the fixed draw is restored afterwards."""
+        if self.BNN._fused_ok() or getattr(self, "_z_redrawn", False):
+            yield
+            return
+        e = self._engine
+        rf = [self.BNN.layers[2 * l] for l in range(self.n_hidden_layers)]
+        saved = [z.clone() for z in e.z]
+        for l, layer in enumerate(rf):
+            if not layer.random_fixed:
+                e.z[l].normal_()
+        self._z_redrawn = True
+        try:
+            yield
+        finally:
+            self._z_redrawn = False
+            for z, keep in zip(e.z, saved):
+                z.copy_(keep)
+
     def U(self, X_batch, Y_batch, data_size, full_bayesian=False, allow_gradient_from_W=True):
         """Minibatch potential  -(log_prior / N + sum_i ll_i / B)."""
-        _, _, tot = self._engine.evaluate(X_batch, Y_batch)
+        with self._z_for_call():
+            _, _, tot = self._engine.evaluate(X_batch, Y_batch)
         B = float(np.shape(X_batch)[0])
         N = float(data_size)
         if not full_bayesian:
@@ -229,12 +254,13 @@ class DGP_RF:
         allow_gradient_from_W=False and hyper=True: the M-step gradients, utils_training.py:341-354)."""
         hyper = full_bayesian if hyper is None else hyper
         e = self._engine
-        tot, gW, gH = e.gradients(X_batch, Y_batch, data_size, hyper=hyper,
-                                  prior_w=allow_gradient_from_W, prior_h=full_bayesian)
-        g = {n: t.view(e.view(n).shape) for n, t in e.named_from_flat(gW, "w").items()}
-        if hyper:
-            g.update({n: t.view(e.view(n).shape) for n, t in e.named_from_flat(gH, "h").items()})
-        return self.U(X_batch, Y_batch, data_size, full_bayesian, allow_gradient_from_W), g
+        with self._z_for_call():                       # U and its gradient share one draw of z
+            tot, gW, gH = e.gradients(X_batch, Y_batch, data_size, hyper=hyper,
+                                      prior_w=allow_gradient_from_W, prior_h=full_bayesian)
+            g = {n: t.view(e.view(n).shape) for n, t in e.named_from_flat(gW, "w").items()}
+            if hyper:
+                g.update({n: t.view(e.view(n).shape) for n, t in e.named_from_flat(gH, "h").items()})
+            return self.U(X_batch, Y_batch, data_size, full_bayesian, allow_gradient_from_W), g
 
     # ---- SG-MCMC (dgp.py:184-216) ---------------------------------------------------------------------
     def sgmcmc_update(self, X_batch, Y_batch, data_size, lr=0.01, momentum_decay=0.95,
@@ -250,6 +276,16 @@ class DGP_RF:
             self._sampler_ready[bool(full_bayesian)] = True
         e = self._engine
         self._step += 1
+        if not self.BNN._fused_ok():                    # random_fixed=False: fresh z for this step (see _z_for_call)
+            with self._z_for_call():
+                return self._sgmcmc_update_impl(X_batch, Y_batch, data_size, lr, momentum_decay, resample_moments,
+                                                temperature, full_bayesian, eps, resample, None)
+        return self._sgmcmc_update_impl(X_batch, Y_batch, data_size, lr, momentum_decay, resample_moments, temperature,
+                                        full_bayesian, eps, resample, u_host)
+
+    def _sgmcmc_update_impl(self, X_batch, Y_batch, data_size, lr, momentum_decay, resample_moments, temperature,
+                            full_bayesian, eps, resample, u_host):
+        e = self._engine
         if (eps is None and resample is None and type(X_batch) is torch.Tensor and type(Y_batch) is torch.Tensor
                 and not X_batch.is_cuda and X_batch.dtype is torch.float32 and Y_batch.dtype is torch.float32
                 and X_batch.dim() == 2 and Y_batch.dim() == 2 and X_batch.is_contiguous() and Y_batch.is_contiguous()
@@ -294,8 +330,9 @@ class DGP_RF:
         mean_h, m2_h = zeros(e.layout.h_len), zeros(e.layout.h_len)
         k = 0
         for X_batch, Y_batch in ds:
-            _, gW, gH = e.gradients(X_batch, Y_batch, data_size, hyper=full_bayesian, prior_w=True,
-                                    prior_h=full_bayesian)
+            with self._z_for_call():
+                _, gW, gH = e.gradients(X_batch, Y_batch, data_size, hyper=full_bayesian, prior_w=True,
+                                        prior_h=full_bayesian)
             k += 1
             _ffi.check(L.dgprf_welford_update(gW.data_ptr(), mean_w.data_ptr(), m2_w.data_ptr(), e.layout.w_len, k, st))
             if full_bayesian:
