@@ -504,6 +504,9 @@ extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* 
 }
 
 // ---- update -----------------------------------------------------------------------------------------
+// the device-resident step base of dgprf_sgmcmc_step_graph, attached to every UpdArgs built during that call
+static thread_local const unsigned long long* g_step_dev = nullptr;
+
 static int fill_upd_args(UpdArgs& a, float* theta, float* mom, int64_t cs, int64_t n,
                          const float* grad, int64_t grad_cs, int n_part, int64_t part_stride,
                          const dgprf_segment* segs, int n_seg, float lr, float data_size, float beta,
@@ -520,6 +523,7 @@ static int fill_upd_args(UpdArgs& a, float* theta, float* mom, int64_t cs, int64
     a.inv_N = 1.f / data_size;
     a.resample = resample; a.seed = seed; a.step = step; a.stream_base = stream_base;
     a.eps_inject = eps_inject; a.mom_inject = mom_inject;
+    a.step_dev = g_step_dev;
     return DGPRF_OK;
 }
 
@@ -545,6 +549,35 @@ extern "C" int dgprf_sgmcmc_update(float* theta, float* mom, int64_t cs, int64_t
     return update_impl(theta, mom, cs, n, n_chains, grad, grad_cs, n_part, part_stride, segs, n_seg, lr, data_size,
                        momentum_decay, temperature, resample_moments, seed, step, 0u, eps_inject, mom_inject,
                        (cudaStream_t)stream);
+}
+
+extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y,
+                                 int64_t y_cs, int B, int full_bayesian,
+                                 float* theta_w, float* mom_w, int64_t w_len,
+                                 const dgprf_segment* segs_w, int n_seg_w,
+                                 float* theta_h, float* mom_h, int64_t h_len,
+                                 const dgprf_segment* segs_h, int n_seg_h,
+                                 float lr, float data_size, float momentum_decay, float temperature,
+                                 int resample_moments, uint64_t seed, uint64_t step,
+                                 const float* eps_w, const float* res_w, const float* eps_h, const float* res_h,
+                                 void* ws, size_t ws_bytes, float* u_out, void* stream);
+
+extern "C" int dgprf_sgmcmc_step_graph(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y,
+                                       int64_t y_cs, int B, int full_bayesian,
+                                       float* theta_w, float* mom_w, int64_t w_len,
+                                       const dgprf_segment* segs_w, int n_seg_w,
+                                       float* theta_h, float* mom_h, int64_t h_len,
+                                       const dgprf_segment* segs_h, int n_seg_h,
+                                       float lr, float data_size, float momentum_decay, float temperature,
+                                       int resample_moments, uint64_t seed, uint64_t step, const uint64_t* step_base_dev,
+                                       void* ws, size_t ws_bytes, float* u_out, void* stream) {
+    DGPRF_REQUIRE(step_base_dev != nullptr, "step_graph: step_base_dev is NULL");
+    g_step_dev = reinterpret_cast<const unsigned long long*>(step_base_dev);
+    const int rc = dgprf_sgmcmc_step(m, X, x_cs, Y, y_cs, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w, theta_h, mom_h,
+                                     h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature, resample_moments, seed,
+                                     step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes, u_out, stream);
+    g_step_dev = nullptr;
+    return rc;
 }
 
 extern "C" int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y,

@@ -24,6 +24,7 @@ struct UpdArgs {
     int32_t resample;
     uint64_t seed, step; uint32_t stream_base;
     const float* eps_inject; const float* mom_inject;
+    const unsigned long long* step_dev;   // nullable: device-resident base added to `step` (CUDA-graph replays draw fresh noise)
 };
 
 struct HypArgs {

@@ -44,14 +44,15 @@ __device__ __forceinline__ float4 shuffle_sum_lpv(float4 g) {
 // waits at its grid barrier): e = the injected / Philox noise (zero at T = 0), m = the resampled momentum if asked.
 __device__ __forceinline__ void sgmcmc_draw_vec(const UpdArgs& a, int chain, int64_t i4, float4& e, float4& m) {
     const int64_t i = i4 << 2;
+    const uint64_t step = a.step + (a.step_dev ? (uint64_t)__ldg(a.step_dev) : 0ull);
     if (a.resample) {
         if (a.mom_inject) m = __ldg(reinterpret_cast<const float4*>(a.mom_inject + chain * a.cs + i));
-        else m = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base + 1u);
+        else m = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, step, a.stream_base + 1u);
     }
     e = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.noise_scale != 0.f) {
         if (a.eps_inject) e = __ldg(reinterpret_cast<const float4*>(a.eps_inject + chain * a.cs + i));
-        else e = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, a.step, a.stream_base);
+        else e = philox_normal4(a.seed, (uint64_t)chain, (uint64_t)i4, step, a.stream_base);
     }
 }
 

@@ -66,6 +66,10 @@ SIGNATURES = {
                                _VP, _VP, _I64, _SP, _I, _VP, _VP, _I64, _SP, _I,
                                _F, _F, _F, _F, _I, _U64, _U64, _VP, _VP, _VP, _VP,
                                _VP, _SZ, _VP, _VP]),
+    "dgprf_sgmcmc_step_graph": (_I, [_MP, _VP, _I64, _VP, _I64, _I, _I,
+                                     _VP, _VP, _I64, _SP, _I, _VP, _VP, _I64, _SP, _I,
+                                     _F, _F, _F, _F, _I, _U64, _U64, _VP,
+                                     _VP, _SZ, _VP, _VP]),
     "dgprf_sgmcmc_step_host": (_I, [_MP, _VP, _VP, _I, _I, _VP, _VP, _I, _I,
                                     _VP, _VP, _I64, _SP, _I, _VP, _VP, _I64, _SP, _I,
                                     _F, _F, _F, _F, _I, _U64, _U64, _VP, _SZ, _VP, _VP, _VP]),

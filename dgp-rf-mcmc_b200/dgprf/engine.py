@@ -313,14 +313,26 @@ class Engine:
 
     def step(self, X, Y, data_size: float, lr: float, momentum_decay: float, temperature: float,
              resample: bool, full_bayesian: bool, seed: int, step: int,
-             eps_w=None, res_w=None, eps_h=None, res_h=None, u_out: Optional[torch.Tensor] = None):
-        """One sgmcmc_update (models/dgp.py:184-216) for all C chains: a single C call."""
+             eps_w=None, res_w=None, eps_h=None, res_h=None, u_out: Optional[torch.Tensor] = None,
+             step_base: Optional[torch.Tensor] = None):
+        """One sgmcmc_update (models/dgp.py:184-216) for all C chains: a single C call.
+        step_base (int64 device scalar): the Philox step becomes step + *step_base (CUDA-graph replays)."""
         m = self.model()
         X, x_cs, Y, y_cs, B = self._xy(X, Y)
         mode = _ffi.MODE_HYPER if full_bayesian else _ffi.MODE_TRAIN
         ws = self.workspace(m, B, mode)
         sw, nsw, sh, nsh = self._segments()
         p = _ffi.ptr
+        if step_base is not None:
+            assert eps_w is None and res_w is None and eps_h is None and res_h is None
+            assert step_base.dtype == torch.int64 and step_base.is_cuda and step_base.numel() == 1
+            _ffi.check(_ffi.lib().dgprf_sgmcmc_step_graph(
+                C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, int(full_bayesian),
+                self.theta_w.data_ptr(), self.mom_w.data_ptr(), self.layout.w_len, sw, nsw,
+                self.theta_h.data_ptr(), self.mom_h.data_ptr(), self.layout.h_len, sh, nsh,
+                float(lr), float(data_size), float(momentum_decay), float(temperature), int(bool(resample)),
+                int(seed), int(step), step_base.data_ptr(), ws.data_ptr(), ws.numel(), p(u_out), _ffi.stream_ptr()))
+            return
         _ffi.check(_ffi.lib().dgprf_sgmcmc_step(
             C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, int(full_bayesian),
             self.theta_w.data_ptr(), self.mom_w.data_ptr(), self.layout.w_len, sw, nsw,

@@ -166,6 +166,22 @@ int dgprf_sgmcmc_step(const dgprf_model* m, const float* X, int64_t x_cs, const 
                       const float* eps_w, const float* res_w, const float* eps_h, const float* res_h,
                       void* ws, size_t ws_bytes, float* u_out, void* stream);
 
+/* dgprf_sgmcmc_step for CUDA-graph capture (the sampler drivers replay one captured epoch per launch,
+ * experiments/utils_training.py:41-66): every argument is baked into the captured kernel nodes, so the Philox
+ * counter would repeat on replay -- here the noise is keyed by step + *step_base_dev, a device-resident
+ * 64-bit base the caller advances between replays (no injected-noise pointers in this variant).  The call
+ * only enqueues kernels on `stream` (no allocation, no synchronisation), so it may be issued while `stream`
+ * is being captured. */
+int dgprf_sgmcmc_step_graph(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y,
+                            int64_t y_cs, int B, int full_bayesian,
+                            float* theta_w, float* mom_w, int64_t w_len,
+                            const dgprf_segment* segs_w, int n_seg_w,
+                            float* theta_h, float* mom_h, int64_t h_len,
+                            const dgprf_segment* segs_h, int n_seg_h,
+                            float lr, float data_size, float momentum_decay, float temperature,
+                            int resample_moments, uint64_t seed, uint64_t step, const uint64_t* step_base_dev,
+                            void* ws, size_t ws_bytes, float* u_out, void* stream);
+
 /* The same step driven from HOST minibatches (the reference's drivers hand numpy / tf.data batches to
  * sgmcmc_update, experiments/utils_training.py:45-61): X_host [B, d_in] and Y_host [B, d_out | 1] are copied
  * to the caller's device staging buffers X_dev / Y_dev with cudaMemcpyAsync on `stream` (pinned host memory

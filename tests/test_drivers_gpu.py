@@ -72,7 +72,7 @@ def test_sampler_driver_follows_the_reference_loop():
         for xb, yb in ds_train:
             _, _, q, mom = O.sgmcmc_step(q, mom, xb.double(), yb.double(), N, lr=0.01, momentum_decay=0.9,
                                          temperature=0.0, full_bayesian=False, eps=None)
-    log_p, mse = regression_train(model, ds_train, ds_test, N, lr_0=0.01, momentum_decay=0.9, full_bayesian=False,
+    log_p, mse = regression_train(model, data=(ds_train, ds_test, N), lr_0=0.01, momentum_decay=0.9, full_bayesian=False,
                                   total_epochs=2 + 2, start_sampling_epoch=2, epochs_per_cycle=2, verbose=False,
                                   resample_in_cycle_head=True)
     assert log_p.shape == (1, 30) and mse.shape == (1, 30)            # one cycle -> one posterior sample

@@ -128,3 +128,43 @@ def test_philox_host_reference_known_answers():
     assert philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_driver_signatures_match_the_reference():
+    """Positional parameter names and defaults of the drivers, as written in the reference
+    (experiments/utils_training.py:11-16, 93-98, 174-177, 258-261, 339, 361-363, 381-383, 431-433;
+    experiments/utils_training_demo.py:10-14, 87-89, 171, 193-195, 215-217)."""
+    import inspect
+    from experiments import utils_training as T, utils_training_demo as D
+
+    def pos(fn):
+        return [(n, p.default) for n, p in inspect.signature(fn).parameters.items()
+                if p.kind is inspect.Parameter.POSITIONAL_OR_KEYWORD]
+
+    train = [("lr_0", 0.01), ("momentum_decay", 0.9), ("full_bayesian", True), ("precond_type", "identity"), ("K_batches", None),
+             ("second_moment_centered", None), ("resample_in_cycle_head", False), ("total_epochs", 5000),
+             ("start_sampling_epoch", 2000), ("epochs_per_cycle", 50), ("print_epoch_cycle", 100)]
+    E = inspect.Parameter.empty
+    assert pos(T.regression_train) == [("model", E), ("dataset_name", "boston"), ("batch_size", 200), ("data_dir", "./data/")] + train
+    assert pos(T.classification_train) == [("model", E), ("dataset_name", "mnist"), ("batch_size", 200),
+                                           ("data_dir", "./tensorflow_datasets/")] + train
+    smp = [("lr_0", 0.01), ("momentum_decay", 0.9), ("precond_type", "identity"), ("K_batches", None),
+           ("second_moment_centered", None), ("resample_in_cycle_head", True), ("start_sampling_epoch", 2000), ("epochs_per_cycle", 50)]
+    assert pos(T.MCEM_sampler_UCI) == [("model", E), ("dataset_name", "boston"), ("batch_size", 200), ("data_dir", "./data/")] + smp
+    assert pos(T.MCEM_sampler_classification)[4:] == smp
+    assert [n for n, _ in pos(T.MCEM_Q_maximizer)] == ["model", "data_size", "optimizer"]
+    em = [("sampler_EM", E), ("maximizer", E), ("sampler_fixing_hyper", E), ("total_EM_steps", E), ("ds_train", E)]
+    assert pos(T.MCEM) == em + [("num_samples_EM", 100), ("num_samples_fixing_hyper", 200), ("print_epoch_cycle_EM", 100),
+                                ("print_epoch_cycle_fixing", 100)]
+    win = em + [("num_samples_fixing_hyper", 200), ("window_size", 300), ("print_epoch_cycle_EM", 100), ("print_epoch_cycle_fixing", 100)]
+    assert pos(T.MCEM_windows) == win and pos(T.MCEM_increasing_windows) == win
+    demo = [("model_demo", E), ("ds_train", E), ("ds_test", E), ("train_size", E), ("batch_size", E), ("X_test", E)]
+    assert pos(D.regression_train_demo) == demo + [("lr_0", 0.01), ("momentum_decay", 0.9), ("resample_in_cycle_head", True),
+                                                   ("total_epochs", 5000), ("start_sampling_epoch", 2000), ("epochs_per_cycle", 50),
+                                                   ("print_epoch_cycle", 100)]
+    assert pos(D.MCEM_sampler_demo) == demo + [("lr_0", 0.01), ("momentum_decay", 0.9), ("resample_in_cycle_head", False),
+                                               ("start_sampling_epoch", 0), ("epochs_per_cycle", 50)]
+    assert [n for n, _ in pos(D.MCEM_Q_maximizer_demo)] == ["model_demo", "data_size", "optimizer"]
+    assert pos(D.MCEM_demo) == pos(T.MCEM)
+    assert pos(D.MCEM_windows_demo) == em + [("num_samples_fixing_hyper", 200), ("window_size", 50), ("print_epoch_cycle_EM", 100),
+                                             ("print_epoch_cycle_fixing", 100)]

@@ -92,7 +92,7 @@ def _gpu_chain(task, seed, X, Y, Xt, Yt, arch, B, lr_0, beta):
                 yield Xd[idx], Yd[idx]
     ds_test = [(Xt.cuda(), Yt.cuda())]
     train = regression_train if task == "reg" else classification_train
-    log_p, aux = train(model, Shuffled(), ds_test, N, lr_0=lr_0, momentum_decay=beta, full_bayesian=False,
+    log_p, aux = train(model, data=(Shuffled(), ds_test, N), lr_0=lr_0, momentum_decay=beta, full_bayesian=False,
                        precond_type='identity', resample_in_cycle_head=False, verbose=False, **SCHED)
     assert log_p.shape[0] == (SCHED["total_epochs"] - SCHED["start_sampling_epoch"]) // SCHED["epochs_per_cycle"]
     return predictive_average(log_p, aux, aux_is_se=(task == "reg"))
