@@ -87,9 +87,15 @@ __device__ __forceinline__ void issue_gemm2(uint32_t tm_d2, uint64_t dphi, uint6
 
 template <int NG, bool WIDE>
 __global__ void __launch_bounds__(V2_THREADS, 1)
-k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW, long long* const tl, const __grid_constant__ CUtensorMap map_cos,
+k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, const __grid_constant__ CUtensorMap map_cos,
            const __grid_constant__ CUtensorMap map_sin, const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt,
            const __grid_constant__ CUtensorMap map_at) {
+    // NSW_ bit 8 (DGPRF_TC2_DIRECT_STORE=1, an experiment kept for A/B runs): the epilogue warps store the saved features
+    // straight from registers (st.global.v4, 64 B per row and half) instead of the store warp's TMA store of the shared
+    // tile.  Measured at configs[4] layer scale: 1.39 ms against 0.65 ms -- a warp-wide store of 32 rows 32 KB apart is 32
+    // separate requests per instruction and partial-sector writes; the coalesced TMA store stays the default.
+    const int NSW = NSW_ & 0xff;
+    const bool direct_store = (NSW_ & 0x100) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* bias_s = reinterpret_cast<float*>(sm);
@@ -260,6 +266,27 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW, long long* const tl, c
                 }
             }
             if (tid == 0) TL(t, 2);
+            if (direct_store && a.Phi != nullptr && row0 + r < a.B) {
+                // saved features from registers: 64 contiguous bytes per row and half (cos | sin); the four column-quarter
+                // warps of a lane quarter fill 256 contiguous bytes of the row between them (merged in L2)
+                float* dst = a.Phi + chain * a.phi_cs + (int64_t)(row0 + r) * a.F + c0 + 16 * cq;
+                if (c0 + 16 * cq + 16 <= a.M) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(p[4 * c4], p[4 * c4 + 1], p[4 * c4 + 2], p[4 * c4 + 3]);
+                        if (rbf)
+                            *reinterpret_cast<float4*>(dst + a.M + 4 * c4) =
+                                make_float4(f1[4 * c4], f1[4 * c4 + 1], f1[4 * c4 + 2], f1[4 * c4 + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + 16 * cq + i < a.M) {
+                            dst[i] = p[i];
+                            if (rbf) dst[a.M + i] = f1[i];
+                        }
+                }
+            }
             tc::mbar_wait(phi_empty, (t & 1) ^ 1);                   // GEMM #2 and the store of tile t-1 are done
             if (tid == 0) TL(t, 3);
 #pragma unroll
@@ -423,7 +450,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW, long long* const tl, c
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (ct0 + t) * V2_BN;
                 tc::mbar_wait(phi_full, t & 1);
-                if (a.Phi != nullptr) {
+                if (a.Phi != nullptr && !direct_store) {
                     for (int b = 0; b < 2; ++b) {
                         if (c0 + 32 * b >= a.M) break;
                         tc::tma_store_3d(&map_cos, tc::smem_u32(sPhi + b * V2_BLK), c0 + 32 * b, row0, chain);
@@ -594,7 +621,7 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     if (rc) return rc;
     static long long* tl = nullptr;
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw, tl, mc, ms, mo, mw, ma); }
+    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0), tl, mc, ms, mo, mw, ma); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -636,7 +663,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2, tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2 | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12];
