@@ -100,15 +100,6 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_peer(const float* local, uint32_t rank) {
-    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-    float v;
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-    return v;
-}
-
 // Same self-resetting grid barrier as K9 (cooperative launch: all CTAs co-resident; bounded spin).
 __device__ __forceinline__ void grid_barrier_cl(unsigned int* bar, unsigned int my_gen, unsigned int n_ctas) {
     __syncthreads();
@@ -129,47 +120,111 @@ __device__ __forceinline__ void grid_barrier_cl(unsigned int* bar, unsigned int 
     __syncthreads();
 }
 
-// Cross-warp + cross-CTA reduction of a per-warp accumulator set acc[MT][kNJ][4] (rows of the cluster's row tile x
-// nt*8 columns): warp partials -> `red`, fixed-order sum over the warps -> this CTA's partial in `fx`, one cluster
-// barrier, fixed-order sum over the CL ranks -> f_s[r][c] (every CTA of the cluster holds the identical result).
-template <int MT>
-__device__ __forceinline__ void reduce_exchange(const float (&acc)[MT][kNJ][4], int nt, float* __restrict__ red, float* __restrict__ fx,
-                                                float* __restrict__ f_s, int ncs, int CL) {
+// ---- cluster exchange: pushed partials, counted by a transaction barrier ------------------------------------------
+// Every CTA owns receive slots rx[2][CL][RT*ncs] (ping-pong x source rank) and two mbarriers.  A sender writes its partial
+// straight into the peers' slots with st.async (a remote shared-memory store that completes `bytes` on the RECEIVER's
+// mbarrier), so the receiver needs no cluster-wide barrier, no gpu-scope fence and no L1 invalidate: it arms its barrier
+// with the byte count it expects and waits on its own shared memory.  (barrier.cluster.arrive.release compiles to
+// MEMBAR.ALL.GPU + ERRBAR and the wait to CCTL.IVALL: ~3000 cycles per exchange in the pull version.)
+// Ping-pong safety: a peer sends exchange n only after it has consumed exchange n-1, which it received from me after I
+// had finished reading exchange n-2 out of the same slots.
+struct Xchg {
+    float* red;              // [kW][RT][ncs] per-warp partials
+    float* rx;               // [2][CL][RT*ncs]
+    uint64_t* bar;           // [2]
+    int ncs, CL, rank;
+    uint32_t n;              // exchanges so far
+};
+__device__ __forceinline__ uint32_t map_peer(const void* local, uint32_t rank) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();           // a lost partial traps instead of hanging the GPU
+    }
+}
+
+// Cross-warp + cross-CTA reduction of a per-warp accumulator set acc[MT][kNJ][4] (rows of the cluster's row tile x nt*8
+// columns).  Warp partials -> `red`, fixed-order sum over the warps = this CTA's partial, pushed to every CTA of the
+// cluster; then every CTA sums the CL partials in rank order (deterministic, identical on all CTAs) and hands element
+// (r, c) to `consume` on the thread that owns it.  The caller synchronises the CTA after its own follow-up work.
+template <int MT, typename Consume>
+__device__ __forceinline__ void reduce_gather(const float (&acc)[MT][kNJ][4], int nt, Xchg& x, Consume&& consume) {
     constexpr int RT = 16 * MT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int ncs = x.ncs, CL = x.CL;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int j = 0; j < kNJ; ++j)
             if (j < nt) {
-                float* p = red + ((warp * RT + mt * 16 + g) * ncs + j * 8 + 2 * t);
+                float* p = x.red + ((warp * RT + mt * 16 + g) * ncs + j * 8 + 2 * t);
                 *reinterpret_cast<float2*>(p) = make_float2(acc[mt][j][0], acc[mt][j][1]);
                 *reinterpret_cast<float2*>(p + 8 * ncs) = make_float2(acc[mt][j][2], acc[mt][j][3]);
             }
     __syncthreads();
     const int nc = nt * 8;
+    const int ph = x.n & 1;
+    float* rxp = x.rx + ph * (CL * RT * ncs);
+    uint64_t* bar = x.bar + ph;
+    if (CL > 1 && tid == 0) mbar_expect_tx(bar, (uint32_t)((CL - 1) * RT * nc * sizeof(float)));
+    uint32_t peer_rx[8], peer_bar[8];
+    if (CL > 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < CL) {
+                peer_rx[k] = map_peer(rxp + x.rank * RT * ncs, (uint32_t)k);     // my slot in CTA k's receive buffer
+                peer_bar[k] = map_peer(bar, (uint32_t)k);
+            }
+    }
     for (int e = tid; e < RT * nc; e += kT) {
         const int r = e / nc, c = e - r * nc;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kW; ++w) s += red[(w * RT + r) * ncs + c];
-        if (CL > 1) fx[r * ncs + c] = s;
-        else f_s[r * kFS + c] = s;
+        for (int w = 0; w < kW; ++w) s += x.red[(w * RT + r) * ncs + c];
+        if (CL == 1) {
+            consume(r, c, s);
+        } else {
+            const int o = r * ncs + c;
+            rxp[x.rank * RT * ncs + o] = s;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < CL && k != x.rank) st_async_f32(peer_rx[k] + 4u * o, s, peer_bar[k]);
+        }
     }
     if (CL > 1) {
-        cluster_sync_all();
+        mbar_wait_parity(bar, (x.n >> 1) & 1);
         for (int e = tid; e < RT * nc; e += kT) {
             const int r = e / nc, c = e - r * nc;
+            const int o = r * ncs + c;
             float pv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) pv[k] = k < CL ? ld_peer(fx + r * ncs + c, (uint32_t)k) : 0.f;    // all in flight
+            for (int k = 0; k < 8; ++k) pv[k] = k < CL ? rxp[k * RT * ncs + o] : 0.f;
             float s = pv[0];
 #pragma unroll
             for (int k = 1; k < 8; ++k) s += pv[k];          // rank order (adding the zeros of absent ranks is exact)
-            f_s[r * kFS + c] = s;
+            consume(r, c, s);
         }
     }
-    __syncthreads();
+    ++x.n;
 }
 
 template <int MT>
@@ -195,12 +250,22 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     float* t_hi  = a_lo + RT * a.lda;                    // [32][LDT]   dF^T (A operand of gW^T = dF^T Phi), hi
     float* t_lo  = t_hi + 32 * LDT;                      //             ... lo
     float* red   = t_lo + 32 * LDT;                      // [kW][RT][ncs] per-warp partials
-    float* fx0   = red + kW * RT * a.ncs;                // [2][RT][ncs] this CTA's partial, read by the cluster (ping-pong)
-    float* phi_all = fx0 + 2 * RT * a.ncs;               // per layer [RT][ldp]
+    float* rx    = red + kW * RT * a.ncs;                // [2][CL][RT][ncs] receive slots of the cluster exchange (CL > 1)
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(rx + (CL > 1 ? 2 * CL * RT * a.ncs : 0));      // [2] transaction barriers (+ pad)
+    float* phi_all = reinterpret_cast<float*>(xbar + 2) ;// per layer [RT][ldp]
 
     const float* X = a.X + chain * a.x_cs;
     const float* Y = a.Y + chain * a.y_cs;
-    int xph = 0;                                         // exchange-buffer parity
+    Xchg xc;
+    xc.red = red; xc.rx = rx; xc.bar = xbar; xc.ncs = a.ncs; xc.CL = CL; xc.rank = rank; xc.n = 0;
+    if (CL > 1) {
+        if (tid == 0) {
+            mbar_init(xbar, 1);
+            mbar_init(xbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();                              // every CTA's barriers exist before the first remote store
+    }
     int tsi = 0;
 #define K10_STAMP() do { if (a.timing && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.timing[tsi] = clock64(); ++tsi; } while (0)
     K10_STAMP();
@@ -238,36 +303,44 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     }
     __syncthreads();
 
+    // A operand of a layer: (in * s) split hi / lo, K zero-padded to a multiple of 8; in = [F_{l-1}, X].  The X part (and
+    // the padding) of layer l is written here, the F part by the consumer of the previous layer's exchange.
+    auto build_x_part = [&](int l) {
+        const ClLayer& y = a.layer[l];
+        const int d = y.d_prev + y.d_x, Kp = (d + 7) & ~7, nx = Kp - y.d_prev;
+        const float* s_s = s_all + l * a.dmax;
+        for (int e = tid; e < RT * nx; e += kT) {
+            const int r = e / nx, q = y.d_prev + (e - r * nx);
+            const float v = q < d ? x_s[r * a.d_in + (q - y.d_prev)] * s_s[q] : 0.f;
+            uint32_t hi, lo;
+            split_tf32(v, hi, lo);
+            a_hi[r * a.lda + q] = __uint_as_float(hi);
+            a_lo[r * a.lda + q] = __uint_as_float(lo);
+        }
+    };
+    auto build_bias = [&](int l) {                       // bias_r = in_r . mean (needs the complete F_{l-1} in f_s)
+        const ClLayer& y = a.layer[l];
+        if (tid < RT) {
+            float b = 0.f;
+            if (y.has_mean) {
+                const float* m_s = m_all + l * a.dmax;
+                for (int q = 0; q < y.d_prev; ++q) b = fmaf(f_s[tid * kFS + q], m_s[q], b);
+                for (int q = y.d_prev; q < y.d_prev + y.d_x; ++q) b = fmaf(x_s[tid * a.d_in + (q - y.d_prev)], m_s[q], b);
+            }
+            bias[tid] = b;
+        }
+    };
+    build_x_part(0);
+    build_bias(0);
+    __syncthreads();
+    K10_STAMP();
+
     // =========================== forward ===========================
     for (int l = 0; l < L; ++l) {
         const ClLayer& y = a.layer[l];
         const int d = y.d_prev + y.d_x, M = y.M, G = y.g;
         const bool rbf = y.kind == DGPRF_KIND_RBF;
         const int Kp = (d + 7) & ~7;
-        const float* s_s = s_all + l * a.dmax;
-        const float* m_s = m_all + l * a.dmax;
-        // ---- A operand: (in * s) split hi / lo, K zero-padded to Kp;  in = [F_{l-1} (f_s), X (x_s)]
-        for (int e = tid; e < RT * Kp; e += kT) {
-            const int r = e / Kp, q = e - r * Kp;
-            float v = 0.f;
-            if (q < y.d_prev) v = f_s[r * kFS + q] * s_s[q];
-            else if (q < d) v = x_s[r * a.d_in + (q - y.d_prev)] * s_s[q];
-            uint32_t hi, lo;
-            split_tf32(v, hi, lo);
-            a_hi[r * a.lda + q] = __uint_as_float(hi);
-            a_lo[r * a.lda + q] = __uint_as_float(lo);
-        }
-        if (tid < RT) {
-            float b = 0.f;
-            if (y.has_mean) {
-                for (int q = 0; q < y.d_prev; ++q) b = fmaf(f_s[tid * kFS + q], m_s[q], b);
-                for (int q = y.d_prev; q < d; ++q) b = fmaf(x_s[tid * a.d_in + (q - y.d_prev)], m_s[q], b);
-            }
-            bias[tid] = b;
-        }
-        __syncthreads();
-        K10_STAMP();
-
         const int c_lo = rank * y.cols, c_hi = min(M, c_lo + y.cols);
         const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
         const float* z = y.z + chain * y.z_cs;
@@ -391,8 +464,25 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                 }
         }
         K10_STAMP();
-        reduce_exchange<MT>(facc, NJ, red, fx0 + xph * RT * a.ncs, f_s, a.ncs, CL);      // f_s = F_l
-        xph ^= 1;
+        {   // F_l = sum of the partials; the owner of element (r, c) also writes the next layer's A operand
+            const bool more = l + 1 < L;
+            const float* s_n = s_all + (more ? l + 1 : l) * a.dmax;
+            reduce_gather<MT>(facc, NJ, xc, [&](int r, int c, float v) {
+                f_s[r * kFS + c] = v;
+                if (more && c < G) {
+                    uint32_t hi, lo;
+                    split_tf32(v * s_n[c], hi, lo);
+                    a_hi[r * a.lda + c] = __uint_as_float(hi);
+                    a_lo[r * a.lda + c] = __uint_as_float(lo);
+                }
+            });
+            if (more) {
+                build_x_part(l + 1);
+                if (a.layer[l + 1].has_mean) __syncthreads();          // the bias needs all of F_l
+                build_bias(l + 1);
+            }
+        }
+        __syncthreads();
         K10_STAMP();
     }
 
@@ -436,42 +526,43 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     K10_STAMP();
 
     // =========================== backward ===========================
+    // element (r, c) of dF_l into the two operand images (zero beyond g: the K / M padding of the MMAs)
+    auto put_dF = [&](int r, int c, float v, int NJ, int MJ) {
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        if (c < NJ * 8) {
+            a_hi[r * a.lda + c] = __uint_as_float(hi);
+            a_lo[r * a.lda + c] = __uint_as_float(lo);
+        }
+        if (c < MJ * 16) {
+            t_hi[c * LDT + r] = __uint_as_float(hi);
+            t_lo[c * LDT + r] = __uint_as_float(lo);
+        }
+    };
     for (int l = L - 1; l >= 0; --l) {
         const ClLayer& y = a.layer[l];
         const int M = y.M, G = y.g;
         const bool rbf = y.kind == DGPRF_KIND_RBF;
         const int NJ = (G + 7) >> 3, MJ = (G + 15) >> 4;
         const int nblk = rbf ? 2 : 1;
-        // ---- dF_l operands.  Top layer: f_s is dU/dF from the likelihood; below: f_s holds the raw T (and rowsum R in
-        //      column g) of the layer above, dF_l = s*T + mean*R with s / mean of layer l+1
-        {
+        // ---- dF_l operands (a_hi / a_lo: A of dPhi = dF W^T; t_hi / t_lo: dF^T, A of gW^T = dF^T Phi).  The top layer's
+        //      come from the likelihood seed in f_s; a lower layer's were written by the consumer of the exchange above
+        //      (or, with a trainable mean, from the raw T | R left in f_s: dF = s*T + mean*R needs the whole row)
+        if (l == L - 1 || a.layer[l + 1].has_mean) {
             const bool raw = l < L - 1;
             const float* s_u = s_all + (l + 1) * a.dmax;
             const float* m_u = m_all + (l + 1) * a.dmax;
-            const bool mean_u = raw && a.layer[l + 1].has_mean;
             for (int e = tid; e < RT * 32; e += kT) {
                 const int r = e >> 5, c = e & 31;
                 float v = 0.f;
                 if (c < G) {
                     v = f_s[r * kFS + c];
-                    if (raw) {
-                        v *= s_u[c];
-                        if (mean_u) v = fmaf(m_u[c], f_s[r * kFS + G], v);
-                    }
+                    if (raw) v = fmaf(m_u[c], f_s[r * kFS + G], v * s_u[c]);
                 }
-                uint32_t hi, lo;
-                split_tf32(v, hi, lo);
-                if (c < NJ * 8) {
-                    a_hi[r * a.lda + c] = __uint_as_float(hi);
-                    a_lo[r * a.lda + c] = __uint_as_float(lo);
-                }
-                if (c < MJ * 16) {
-                    t_hi[c * LDT + r] = __uint_as_float(hi);
-                    t_lo[c * LDT + r] = __uint_as_float(lo);
-                }
+                put_dF(r, c, v, NJ, MJ);
             }
+            __syncthreads();
         }
-        __syncthreads();
         K10_STAMP();
 
         const int c_lo = rank * y.cols, c_hi = min(M, c_lo + y.cols);
@@ -619,8 +710,23 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         }
         K10_STAMP();
         if (l == 0) break;
-        reduce_exchange<MT>(tacc, NQ, red, fx0 + xph * RT * a.ncs, f_s, a.ncs, CL);      // f_s = raw T_l (| R_l)
-        xph ^= 1;
+        {   // T_l (| R_l) = sum of the partials; without a trainable mean the owner of (r, c) writes dF_{l-1} = s * T straight
+            // into the operand images of the next backward step
+            const ClLayer& yp = a.layer[l - 1];
+            const int Gp = yp.g, NJp = (Gp + 7) >> 3, MJp = (Gp + 15) >> 4;
+            const float* s_l = s_all + l * a.dmax;
+            const bool direct = !y.has_mean;
+            reduce_gather<MT>(tacc, NQ, xc, [&](int r, int c, float v) {
+                if (direct) put_dF(r, c, c < Gp ? v * s_l[c] : 0.f, NJp, MJp);
+                else f_s[r * kFS + c] = v;
+            });
+            if (direct)                                   // operand rows / columns beyond the exchanged width
+                for (int e = tid; e < RT * (32 - NQ * 8); e += kT) {
+                    const int r = e / (32 - NQ * 8), c = NQ * 8 + (e - r * (32 - NQ * 8));
+                    put_dF(r, c, 0.f, NJp, MJp);
+                }
+        }
+        __syncthreads();
         K10_STAMP();
     }
 
@@ -676,8 +782,6 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             if (tid == 0) a.u_out[chain] = s;
         }
         K10_STAMP();
-    } else if (CL > 1) {
-        cluster_sync_all();          // no CTA may exit while a peer can still read its exchange buffer
     }
 #undef K10_STAMP
 }
@@ -710,7 +814,7 @@ size_t plan_smem(const dgprf_model* m, int MT, int CL, int* lda_out, int* dmax_o
     if (dmax_out) *dmax_out = (int)dmax;
     if (ncs_out) *ncs_out = (int)ncs;
     const int64_t fl = round_up((int64_t)RT * m->d_in, 4) + round_up((int64_t)RT * kFS, 4) + RT + 2 * dmax * m->n_layers +
-                       2 * (int64_t)RT * lda + 2 * 32 * (RT + 4) + (int64_t)kW * RT * ncs + 2 * (int64_t)RT * ncs + phis;
+                       2 * (int64_t)RT * lda + 2 * 32 * (RT + 4) + (int64_t)kW * RT * ncs + (CL > 1 ? 2 * (int64_t)CL * RT * ncs : 0) + 4 + phis;
     return sizeof(float) * (size_t)fl;
 }
 
@@ -890,7 +994,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
         long long h[64];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const int n = 1 + 3 * m->n_layers + 1 + 3 * m->n_layers - 1 + (a.fuse_update ? 2 : 0);
+        const int n = 5 * m->n_layers + 2 + (a.fuse_update ? 2 : 0);      // stamps: start, setup, 2 per forward layer, seed, 3 per backward layer (-1), update
         fprintf(stderr, "k10 (MT %d, CL %d, grid %u) phase cycles:", p.MT, p.CL, grid.x);
         for (int i = 1; i < n; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
         fprintf(stderr, "  total %lld\n", h[n - 1] - h[0]);
