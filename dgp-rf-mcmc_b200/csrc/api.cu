@@ -655,13 +655,47 @@ extern "C" int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host,
     DGPRF_REQUIRE(m && X_host && Y_host && X_dev && Y_dev && B >= 1 && y_cols >= 1, "step_host: bad arguments");
     DGPRF_REQUIRE(u_host == nullptr || u_dev != nullptr, "step_host: u_host needs the u_dev staging word");
     cudaStream_t st = (cudaStream_t)stream;
-    if (zero_copy)       // pinned host buffers are device-visible: no staging copies, one launch
+    if (zero_copy == 1)  // pinned host buffers are device-visible: no staging copies, the kernels read them over the bus
         return dgprf_sgmcmc_step(m, X_host, 0, Y_host, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,
                                  theta_h, mom_h, h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature,
                                  resample_moments, seed, step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes,
                                  u_host, stream);
-    DGPRF_CHECK_CUDA(cudaMemcpyAsync(X_dev, X_host, sizeof(float) * (size_t)B * m->d_in, cudaMemcpyHostToDevice, st));
-    DGPRF_CHECK_CUDA(cudaMemcpyAsync(Y_dev, Y_host, sizeof(float) * (size_t)B * y_cols, cudaMemcpyHostToDevice, st));
+    const size_t xb = sizeof(float) * (size_t)B * m->d_in, yb = sizeof(float) * (size_t)B * y_cols;
+    if (zero_copy == 2) {
+        // Pipelined staging: the minibatch of step n+1 is copied on a side stream into the other half of the (double-sized)
+        // staging buffers while the kernels of step n run; the step's kernels wait on the copy's event, and the copy that
+        // re-uses a half waits on the event recorded after the step that read it.  The side stream and the four events are
+        // the only resources this library ever creates (once per thread and device, never freed).
+        struct Pipe { cudaStream_t cs; cudaEvent_t copied[2], freed[2]; int dev; unsigned n; bool ok; };
+        static thread_local Pipe pl = {nullptr, {nullptr, nullptr}, {nullptr, nullptr}, -1, 0u, false};
+        int dev = 0;
+        DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (!pl.ok || pl.dev != dev) {
+            DGPRF_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.cs, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                DGPRF_CHECK_CUDA(cudaEventCreateWithFlags(&pl.copied[i], cudaEventDisableTiming));
+                DGPRF_CHECK_CUDA(cudaEventCreateWithFlags(&pl.freed[i], cudaEventDisableTiming));
+            }
+            pl.dev = dev; pl.n = 0; pl.ok = true;
+        }
+        const int slot = (int)(pl.n++ & 1u);
+        float* Xs = X_dev + (size_t)slot * B * m->d_in;
+        float* Ys = Y_dev + (size_t)slot * B * y_cols;
+        DGPRF_CHECK_CUDA(cudaStreamWaitEvent(pl.cs, pl.freed[slot], 0));        // a never-recorded event counts as complete
+        DGPRF_CHECK_CUDA(cudaMemcpyAsync(Xs, X_host, xb, cudaMemcpyHostToDevice, pl.cs));
+        DGPRF_CHECK_CUDA(cudaMemcpyAsync(Ys, Y_host, yb, cudaMemcpyHostToDevice, pl.cs));
+        DGPRF_CHECK_CUDA(cudaEventRecord(pl.copied[slot], pl.cs));
+        DGPRF_CHECK_CUDA(cudaStreamWaitEvent(st, pl.copied[slot], 0));
+        const int rc = dgprf_sgmcmc_step(m, Xs, 0, Ys, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,
+                                         theta_h, mom_h, h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature,
+                                         resample_moments, seed, step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes,
+                                         u_host /* pinned: written in place by the kernel */, stream);
+        if (rc) return rc;
+        DGPRF_CHECK_CUDA(cudaEventRecord(pl.freed[slot], st));
+        return DGPRF_OK;
+    }
+    DGPRF_CHECK_CUDA(cudaMemcpyAsync(X_dev, X_host, xb, cudaMemcpyHostToDevice, st));
+    DGPRF_CHECK_CUDA(cudaMemcpyAsync(Y_dev, Y_host, yb, cudaMemcpyHostToDevice, st));
     const int rc = dgprf_sgmcmc_step(m, X_dev, 0, Y_dev, 0, B, full_bayesian, theta_w, mom_w, w_len, segs_w, n_seg_w,
                                      theta_h, mom_h, h_len, segs_h, n_seg_h, lr, data_size, momentum_decay, temperature,
                                      resample_moments, seed, step, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes,

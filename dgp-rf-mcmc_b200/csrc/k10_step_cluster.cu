@@ -952,7 +952,11 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     SegTable tab;
     memset(&tab, 0, sizeof(tab));
     *fused = false;
-    if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE")) {
+    // Nsight Compute cannot replay a launch that is both cooperative and clustered (LaunchFailed, which kills the process):
+    // under its injection the clustered geometries run unfused (K10 + K5), everything else is unchanged.
+    static const bool under_ncu = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+                                  getenv("NV_NSIGHT_INJECTION_PORT_BASE");
+    if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE") && !(under_ncu && p.CL > 1)) {
         static int cached[16][3][9];                     // [device][MT][CL] -> co-resident CTAs + 1 (0: not yet queried) ...
         static size_t cached_smem[16][3][9];             // ... for this shared-memory size
         int dev = 0;

@@ -370,8 +370,8 @@ class Engine:
             m = self.model()
             mode = _ffi.MODE_HYPER if full_bayesian else _ffi.MODE_TRAIN
             ws = self.workspace(m, B, mode)
-            xd = torch.empty(B, dx, device=self.device)
-            yd = torch.empty(B, yc, device=self.device)
+            xd = torch.empty(2 * B, dx, device=self.device)        # two halves: pipelined staging (zero_copy mode 2)
+            yd = torch.empty(2 * B, yc, device=self.device)
             ud = torch.zeros(max(1, self.C), device=self.device)
             sw, nsw, sh, nsh = self._segments()
             fn = _ffi.lib().dgprf_sgmcmc_step_host
@@ -390,10 +390,13 @@ class Engine:
             return self.step_host(X_host, Y_host, data_size, lr, momentum_decay, temperature, resample, full_bayesian,
                                   seed, step, u_host)
         fn, head, mid, tail = st[0], st[1], st[2], st[3]
-        # pinned host tensors are read in place by the kernels (zero-copy); pageable ones go through staging copies
-        zc = 1 if (X_host.is_pinned() and Y_host.is_pinned() and (u_host is None or u_host.is_pinned())) else 0
+        # pinned host tensors: copied on a side stream under the previous step's kernels (mode 2; DGPRF_ZERO_COPY_READ=1:
+        # read in place by the kernels, mode 1); pageable ones go through in-order staging copies (mode 0)
+        zc = 2 if (X_host.is_pinned() and Y_host.is_pinned() and (u_host is None or u_host.is_pinned())) else 0
         if zc and os.environ.get("DGPRF_NO_ZERO_COPY"):
             zc = 0
+        elif zc and os.environ.get("DGPRF_ZERO_COPY_READ"):
+            zc = 1
         rc = fn(*head, X_host.data_ptr(), Y_host.data_ptr(), *mid[0], zc, *mid[1], lr, data_size, momentum_decay, temperature,
                 1 if resample else 0, seed, step, *tail, u_host.data_ptr() if u_host is not None else None,
                 torch.cuda.current_stream().cuda_stream)

@@ -187,9 +187,14 @@ int dgprf_sgmcmc_step_graph(const dgprf_model* m, const float* X, int64_t x_cs, 
  * to the caller's device staging buffers X_dev / Y_dev with cudaMemcpyAsync on `stream` (pinned host memory
  * makes them truly asynchronous), the step runs, and sum_i ll_i is copied back to u_host (nullable; u_dev is
  * its device staging word).  One chain-shared minibatch (x_cs = y_cs = 0).  Nothing synchronises.
- * zero_copy != 0: the host buffers are pinned (page-locked, device-visible under UVA): the kernels read the
- * minibatch straight from host memory over PCIe/NVLink-C2C and write sum_i ll_i straight to u_host -- the same
- * bytes cross the bus inside the step, without the three cudaMemcpyAsync calls (~9 us of CPU time each). */
+ * zero_copy == 1: the host buffers are pinned (page-locked, device-visible under UVA): the kernels read the
+ * minibatch straight from host memory over PCIe/NVLink-C2C and write sum_i ll_i straight to u_host -- no copy
+ * calls, but every CTA's reads are bus round trips inside the step (+9 us per step at BASELINE configs[1]).
+ * zero_copy == 2 (pinned buffers; X_dev / Y_dev hold TWO minibatches): pipelined staging -- the H2D copies of
+ * step n+1 run on a side stream under the kernels of step n (events order the two halves of the staging
+ * buffers), the kernels read device memory, sum_i ll_i is still written in place to the pinned u_host.  The side
+ * stream and its four events are created on first use, once per thread and device: the one exception to
+ * "the library allocates nothing". */
 int dgprf_sgmcmc_step_host(const dgprf_model* m, const float* X_host, const float* Y_host, int y_cols, int B,
                            float* X_dev, float* Y_dev, int zero_copy, int full_bayesian,
                            float* theta_w, float* mom_w, int64_t w_len,
