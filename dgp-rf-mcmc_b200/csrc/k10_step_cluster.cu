@@ -46,6 +46,7 @@ struct ClLayer {
 
 struct ClArgs {
     int32_t n_layers, likelihood, B, d_in, d_out, CL, lda, dmax, ncs;
+    int32_t x_in_smem;                       // the [RT, d_in] input rows are staged in shared memory (small d_in); else read from L2
     int64_t h_cs, w_cs;
     const float* X; int64_t x_cs;
     const float* Y; int64_t y_cs;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     if (a.fuse_update && tid == 0) my_gen = *reinterpret_cast<volatile unsigned int*>(a.bar + 1);
 
     float* x_s   = sm;                                   // [RT][d_in]
-    float* f_s   = x_s + ((RT * a.d_in + 3) & ~3);       // [RT][kFS]   F_l / dF_l / raw T_l (fp32)
+    float* f_s   = x_s + (a.x_in_smem ? ((RT * a.d_in + 3) & ~3) : 0);       // [RT][kFS]   F_l / dF_l / raw T_l (fp32)
     float* bias  = f_s + ((RT * kFS + 3) & ~3);          // [RT]        in . mean (forward); per-row log-likelihood
     float* s_all = bias + RT;                            // [L][dmax]   exp(log_inv_ls)
     float* m_all = s_all + L * a.dmax;                   // [L][dmax]   mean
@@ -290,10 +291,16 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(W + ((int64_t)b * y.M + c_lo) * y.g + 32 * i));
         }
     }
-    for (int e = tid; e < RT * a.d_in; e += kT) {
-        const int r = e / a.d_in, q = e - r * a.d_in;
-        x_s[e] = (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
-    }
+    if (a.x_in_smem)
+        for (int e = tid; e < RT * a.d_in; e += kT) {
+            const int r = e / a.d_in, q = e - r * a.d_in;
+            x_s[e] = (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
+        }
+    // wide inputs (the MNIST-shaped configs) are not staged: every layer reads its X columns from L2
+    auto x_at = [&](int r, int q) -> float {
+        if (a.x_in_smem) return x_s[r * a.d_in + q];
+        return (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
+    };
     for (int e = tid; e < L * a.dmax; e += kT) {
         const int l = e / a.dmax, q = e - l * a.dmax;
         const ClLayer& y = a.layer[l];
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         const float* s_s = s_all + l * a.dmax;
         for (int e = tid; e < RT * nx; e += kT) {
             const int r = e / nx, q = y.d_prev + (e - r * nx);
-            const float v = q < d ? x_s[r * a.d_in + (q - y.d_prev)] * s_s[q] : 0.f;
+            const float v = q < d ? x_at(r, q - y.d_prev) * s_s[q] : 0.f;
             uint32_t hi, lo;
             split_tf32(v, hi, lo);
             a_hi[r * a.lda + q] = __uint_as_float(hi);
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             if (y.has_mean) {
                 const float* m_s = m_all + l * a.dmax;
                 for (int q = 0; q < y.d_prev; ++q) b = fmaf(f_s[tid * kFS + q], m_s[q], b);
-                for (int q = y.d_prev; q < y.d_prev + y.d_x; ++q) b = fmaf(x_s[tid * a.d_in + (q - y.d_prev)], m_s[q], b);
+                for (int q = y.d_prev; q < y.d_prev + y.d_x; ++q) b = fmaf(x_at(tid, q - y.d_prev), m_s[q], b);
             }
             bias[tid] = b;
         }
@@ -795,6 +802,8 @@ int layer_ldp(int kind, int cols) {
     return Fl + ((Fl % 16) == 0 ? 8 : 16);
 }
 
+bool x_staged(const dgprf_model* m, int MT) { return (int64_t)16 * MT * m->d_in <= 4096; }     // <= 16 KB of input rows
+
 size_t plan_smem(const dgprf_model* m, int MT, int CL, int* lda_out, int* dmax_out, int* ncs_out) {
     const int RT = 16 * MT;
     int64_t dmax = 1, kpmax = 32, ncs = 8, phis = 0;
@@ -813,7 +822,7 @@ size_t plan_smem(const dgprf_model* m, int MT, int CL, int* lda_out, int* dmax_o
     if (lda_out) *lda_out = lda;
     if (dmax_out) *dmax_out = (int)dmax;
     if (ncs_out) *ncs_out = (int)ncs;
-    const int64_t fl = round_up((int64_t)RT * m->d_in, 4) + round_up((int64_t)RT * kFS, 4) + RT + 2 * dmax * m->n_layers +
+    const int64_t fl = (x_staged(m, MT) ? round_up((int64_t)RT * m->d_in, 4) : 0) + round_up((int64_t)RT * kFS, 4) + RT + 2 * dmax * m->n_layers +
                        2 * (int64_t)RT * lda + 2 * 32 * (RT + 4) + (int64_t)kW * RT * ncs + (CL > 1 ? 2 * (int64_t)CL * RT * ncs : 0) + 4 + phis;
     return sizeof(float) * (size_t)fl;
 }
@@ -834,23 +843,30 @@ bool make_plan(const dgprf_model* m, int B, ClPlan* p) {
     static const int cap[9] = {0, 148, 148, 0, 128, 0, 0, 0, 112};     // co-resident CTAs per cluster size (1 CTA / SM)
     long best_cost = -1;
     ClPlan best = {0, 0, 0, 0};
-    for (int MT = 2; MT >= 1; --MT)
-        for (int CL = 1; CL <= 8; CL *= 2) {
-            if (e_mt && atoi(e_mt) != MT) continue;
-            if (e_cl && atoi(e_cl) != CL) continue;
-            const int n_tiles = ceil_div(B, 16 * MT);
-            if ((int64_t)n_tiles * CL > cap[CL] && !(e_mt && e_cl)) continue;
-            const size_t smem = plan_smem(m, MT, CL, nullptr, nullptr, nullptr);
-            if (smem > 227 * 1024) continue;
-            // critical path ~ tiles a warp walks per GEMM chain
-            const long per_warp = ceil_div(ceil_div(layer_cols(Mmax, CL), 8), kW);
-            // (x 16 MT rows each), the operand round trips of those tiles, and a charge per cluster exchange
-            const long cost = 16 * MT * per_warp + 4 * per_warp + (CL > 1 ? 2 + CL / 2 : 0);
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                best.MT = MT; best.CL = CL; best.n_tiles = n_tiles; best.smem = smem;
+    // pass 0: geometries whose whole grid is co-resident (one wave: the update can be fused behind the grid barrier);
+    // pass 1: larger minibatches run the same kernel over several waves (stand-alone update), as long as the number of
+    //         gradient slabs (one per row tile) stays small enough for the update to sum
+    for (int pass = 0; pass < 2 && best_cost < 0; ++pass)
+        for (int MT = 2; MT >= 1; --MT)
+            for (int CL = 1; CL <= 8; CL *= 2) {
+                if (e_mt && atoi(e_mt) != MT) continue;
+                if (e_cl && atoi(e_cl) != CL) continue;
+                const int n_tiles = ceil_div(B, 16 * MT);
+                const bool forced = e_mt && e_cl;
+                if (pass == 0 && (int64_t)n_tiles * CL > cap[CL] && !forced) continue;
+                if (pass == 1 && (n_tiles > 256 || getenv("DGPRF_K10_ONE_WAVE"))) continue;
+                const size_t smem = plan_smem(m, MT, CL, nullptr, nullptr, nullptr);
+                if (smem > 227 * 1024) continue;
+                // critical path ~ tiles a warp walks per GEMM chain (x 16 MT rows each), the operand round trips of those
+                // tiles, a charge per cluster exchange -- times the number of waves
+                const long per_warp = ceil_div(ceil_div(layer_cols(Mmax, CL), 8), kW);
+                const long waves = ceil_div((int64_t)n_tiles * CL, cap[CL]);
+                const long cost = waves * (16 * MT * per_warp + 4 * per_warp + (CL > 1 ? 2 + CL / 2 : 0));
+                if (best_cost < 0 || cost < best_cost) {
+                    best_cost = cost;
+                    best.MT = MT; best.CL = CL; best.n_tiles = n_tiles; best.smem = smem;
+                }
             }
-        }
     if (best_cost < 0) return false;
     *p = best;
     return true;
@@ -934,7 +950,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     a.inv_B = 1.f / (float)B;
     int lda = 0, dmax = 0, ncs = 0;
     const size_t smem = plan_smem(m, p.MT, p.CL, &lda, &dmax, &ncs);
-    a.lda = lda; a.dmax = dmax; a.ncs = ncs;
+    a.lda = lda; a.dmax = dmax; a.ncs = ncs; a.x_in_smem = x_staged(m, p.MT) ? 1 : 0;
     int64_t phis = 0;
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];

@@ -83,22 +83,26 @@ def data_parallel_step(engine, X_local: torch.Tensor, Y_local: torch.Tensor, glo
                        seed: int = 0, step: int = 0, group=None) -> torch.Tensor:
     """One W-only sgmcmc_update (models/dgp.py:184-216) of a minibatch whose rows are split over the ranks.
 
-    Every rank runs forward / likelihood seed / backward on its rows (CUDA kernels, data term only), scales the
-    flat gradient by B_local / B_global, joins ONE all-reduce(sum) of [gW | sum_i ll_i], and applies the update
+    Every rank runs forward / likelihood seed / backward on its rows (CUDA kernels, data term only) with the seed scaled
+    by 1 / B_global, so its flat gradient is already its share of the global one; ONE all-reduce(sum) of
+    [gW | sum_i ll_i] (written in place by the kernels, no staging copy), and every rank applies the update
     kernel to its replica with the same Philox (seed, step): the prior term theta/N is added inside the update,
     once, after the reduction; replicas stay bit-identical without a broadcast.  Returns sum_i ll_i [C]."""
-    import ctypes as C
     from . import _ffi
-    tot, gW, _ = engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False)
-    Cn, w_len = gW.shape
-    flat = torch.empty(Cn * w_len + Cn, device=gW.device, dtype=torch.float32)
-    torch.mul(gW.reshape(-1), dp_scale(X_local.shape[0], global_rows), out=flat[:Cn * w_len])
-    flat[Cn * w_len:] = tot
+    w_len = engine.layout.w_len
+    assert engine.C == 1, "the data-parallel step drives one replica per rank"
+    flat = getattr(engine, "_dp_flat", None)
+    if flat is None:
+        flat = engine._dp_flat = torch.empty(w_len + 1, device=engine.device, dtype=torch.float32)
+    # forward / seed / backward of the local rows with the seed already scaled by 1 / B_global: the flat buffer
+    # [gW | sum_i ll_i] is written in place by the kernels and is the all-reduce payload as it stands
+    engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False, inv_B=1.0 / float(global_rows),
+                     out_flat=flat)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     sw, nsw, _, _ = engine._segments()
     _ffi.check(_ffi.lib().dgprf_sgmcmc_update(
-        engine.theta_w.data_ptr(), engine.mom_w.data_ptr(), w_len, w_len, Cn, flat.data_ptr(), w_len, 1, 0,
+        engine.theta_w.data_ptr(), engine.mom_w.data_ptr(), w_len, w_len, 1, flat.data_ptr(), w_len, 1, 0,
         sw, nsw, float(lr), float(data_size), float(momentum_decay), float(temperature), int(bool(resample)),
         int(seed), int(step), None, None, _ffi.stream_ptr()))
-    return flat[Cn * w_len:]
+    return flat[w_len:]

@@ -286,7 +286,7 @@ class Engine:
         return ll, aux, tot
 
     def gradients(self, X, Y, data_size: float, hyper: bool, prior_w: bool, prior_h: bool,
-                  m: Optional[_ffi.Model] = None):
+                  m: Optional[_ffi.Model] = None, inv_B: Optional[float] = None, out_flat: Optional[torch.Tensor] = None):
         """Forward + likelihood seed + backward; returns (ll_sum [C], gW [C,w_len], gH [C,h_len]|None).
         gW/gH are dU/dtheta of models/dgp.py:161-182 (prior terms theta/N added on request)."""
         assert prior_w or not prior_h, "hyper prior without W prior is not a mode of the reference"
@@ -297,13 +297,20 @@ class Engine:
         L = _ffi.lib()
         st = _ffi.stream_ptr()
         Cn = m.n_chains
-        tot = torch.empty(Cn, device=self.device, dtype=torch.float32)
-        gW = torch.empty(Cn, self.layout.w_len, device=self.device, dtype=torch.float32)
+        if out_flat is not None:
+            # data-parallel step: gW and sum_i ll_i land in ONE flat buffer [w_len + 1] (the all-reduce payload); inv_B is the
+            # 1 / B_global the likelihood seed is scaled by (models/dgp.py:174 over the GLOBAL minibatch)
+            assert Cn == 1 and out_flat.numel() == self.layout.w_len + 1 and out_flat.is_contiguous()
+            gW = out_flat[:self.layout.w_len].view(1, -1)
+            tot = out_flat[self.layout.w_len:]
+        else:
+            tot = torch.empty(Cn, device=self.device, dtype=torch.float32)
+            gW = torch.empty(Cn, self.layout.w_len, device=self.device, dtype=torch.float32)
         gH = torch.empty(Cn, self.layout.h_len, device=self.device, dtype=torch.float32) if hyper else None
         a = (C.byref(m),)
         _ffi.check(L.dgprf_forward(*a, X.data_ptr(), x_cs, B, mode, ws.data_ptr(), ws.numel(), None, st))
         _ffi.check(L.dgprf_loglik(*a, Y.data_ptr(), y_cs, B, mode, ws.data_ptr(), ws.numel(), None, None,
-                                  tot.data_ptr(), 1.0 / B, st))
+                                  tot.data_ptr(), (1.0 / B) if inv_B is None else float(inv_B), st))
         _ffi.check(L.dgprf_backward(*a, X.data_ptr(), x_cs, B, mode, ws.data_ptr(), ws.numel(), st))
         inv_N = 1.0 / float(data_size)
         _ffi.check(L.dgprf_grad_finalize(*a, B, mode, ws.data_ptr(), ws.numel(), gW.data_ptr(), gW.shape[1],
