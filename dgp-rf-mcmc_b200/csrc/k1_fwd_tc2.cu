@@ -94,22 +94,26 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     // straight from registers (st.global.v4, 64 B per row and half) instead of the store warp's TMA store of the shared
     // tile.  Measured at configs[4] layer scale: 1.39 ms against 0.65 ms -- a warp-wide store of 32 rows 32 KB apart is 32
     // separate requests per instruction and partial-sector writes; the coalesced TMA store stays the default.
+    // NSW_ bit 9: TWO Phi tiles in shared memory (the launcher then gives the z ring one stage instead of two): the TMA store
+    // of tile t reads its tile while the epilogue writes tile t+1 into the other one.  With one tile the period of a tile is
+    // "store reads 64 KB" + "epilogue writes 64 KB" back to back (profiles/r02_summary.md section B).
     const int NSW = NSW_ & 0xff;
     const bool direct_store = (NSW_ & 0x100) != 0;
+    const int NPHI = (NSW_ & 0x200) ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* bias_s = reinterpret_cast<float*>(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_BM * sizeof(float));
     uint8_t* sPhi = sm + V2_HDR;                         // 4 blocks [128 x 32]: cos 0,1 | sin 2,3
-    uint8_t* sW = sPhi + 4 * V2_BLK;                     // NSW stages x 4 blocks [NG x 32]
+    uint8_t* sW = sPhi + NPHI * 4 * V2_BLK;              // NSW stages x 4 blocks [NG x 32]
     uint8_t* sB1 = sW + NSW * 4 * NG * 128;              // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
                                                          // WIDE: NS1 k-block slots of V2_RING bytes
     uint64_t* b1_full = bars + 0;     // [3] TMA complete_tx      -> MMA
     uint64_t* b1_empty = bars + 3;    // [3] MMA commit           -> producer
     uint64_t* d1_full = bars + 6;     // [2] MMA commit           -> epilogue
     uint64_t* d1_empty = bars + 8;    // [2] epilogue warps       -> MMA
-    uint64_t* phi_full = bars + 10;   // epilogue warps           -> MMA, store
-    uint64_t* phi_empty = bars + 11;  // MMA commit + store warp  -> epilogue      (count 2)
+    uint64_t* phi_full = bars + 18;   // [2] epilogue warps           -> MMA, store
+    uint64_t* phi_empty = bars + 20;  // [2] MMA commit + store warp  -> epilogue      (count 2)
     uint64_t* w_full = bars + 12;     // [2] TMA complete_tx      -> MMA
     uint64_t* w_empty = bars + 14;    // [2] MMA commit           -> producer
     uint64_t* d2_full = bars + 16;    // MMA commit               -> final epilogue
@@ -146,8 +150,10 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             tc::mbar_init(w_full + i, 1);
             tc::mbar_init(w_empty + i, 1);
         }
-        tc::mbar_init(phi_full, V2_EPI_WARPS);
-        tc::mbar_init(phi_empty, 2);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(phi_full + i, V2_EPI_WARPS);
+            tc::mbar_init(phi_empty + i, 2);
+        }
         tc::mbar_init(d2_full, 1);
         tc::mbar_fence_init();
     }
@@ -287,19 +293,21 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                         }
                 }
             }
-            tc::mbar_wait(phi_empty, (t & 1) ^ 1);                   // GEMM #2 and the store of tile t-1 are done
+            const int pbuf = t % NPHI;
+            uint8_t* sPhiT = sPhi + pbuf * 4 * V2_BLK;
+            tc::mbar_wait(phi_empty + pbuf, ((t / NPHI) & 1) ^ 1);   // GEMM #2 and the store of the tile last held here are done
             if (tid == 0) TL(t, 3);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-                *reinterpret_cast<float4*>(sPhi + pb * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
+                *reinterpret_cast<float4*>(sPhiT + pb * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
                     make_float4(p[4 * c4], p[4 * c4 + 1], p[4 * c4 + 2], p[4 * c4 + 3]);
                 if (rbf)
-                    *reinterpret_cast<float4*>(sPhi + (2 + pb) * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
+                    *reinterpret_cast<float4*>(sPhiT + (2 + pb) * V2_BLK + tc::sw128_chunk(r, pc + c4)) =
                         make_float4(f1[4 * c4], f1[4 * c4 + 1], f1[4 * c4 + 2], f1[4 * c4 + 3]);
             }
             tc::fence_async_smem();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(phi_full);
+            if (lane == 0) tc::mbar_arrive(phi_full + pbuf);
             if (tid == 0) TL(t, 4);
         }
         // ---- final: F partial slab of this column split ----
@@ -383,18 +391,20 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
         const uint64_t dW = tc::make_desc_sw128(tc::smem_u32(sW));
         for (int u = 0; u < n_my; ++u) {
             const int ws = u % NSW;
-            tc::mbar_wait(phi_full, u & 1);
+            const int pbuf = u % NPHI;
+            tc::mbar_wait(phi_full + pbuf, (u / NPHI) & 1);
             if (a.do_gemm2) tc::mbar_wait(w_full + ws, (u / NSW) & 1);
             if (lane == 0) TL(u, 7);
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 if (a.do_gemm2) {
                     const uint64_t dw = dW + (uint32_t)((ws * 4 * NG * 128) >> 4);
-                    if (rbf) issue_gemm2<4, NG>(tm_d2, dPhi, dw, IDESC2, u != 0 ? 1u : 0u);
-                    else issue_gemm2<2, NG>(tm_d2, dPhi, dw, IDESC2, u != 0 ? 1u : 0u);
+                    const uint64_t dphi = dPhi + (uint32_t)((pbuf * 4 * V2_BLK) >> 4);
+                    if (rbf) issue_gemm2<4, NG>(tm_d2, dphi, dw, IDESC2, u != 0 ? 1u : 0u);
+                    else issue_gemm2<2, NG>(tm_d2, dphi, dw, IDESC2, u != 0 ? 1u : 0u);
                     tc::umma_commit(w_empty + ws);
                 }
-                tc::umma_commit(phi_empty);            // Phi tile consumed by the tensor core (1 of 2 arrivals)
+                tc::umma_commit(phi_empty + pbuf);     // Phi tile consumed by the tensor core (1 of 2 arrivals)
                 if (u == n_my - 1) tc::umma_commit(d2_full);
             }
             __syncwarp();
@@ -447,19 +457,29 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     } else {
         // ===================================== STORE WARP =====================================
         if (tc::elect_one()) {
+            const bool storing = a.Phi != nullptr && !direct_store;
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (ct0 + t) * V2_BN;
-                tc::mbar_wait(phi_full, t & 1);
-                if (a.Phi != nullptr && !direct_store) {
+                const int pbuf = t % NPHI;
+                tc::mbar_wait(phi_full + pbuf, (t / NPHI) & 1);
+                if (storing) {
+                    const uint8_t* sPhiT = sPhi + pbuf * 4 * V2_BLK;
                     for (int b = 0; b < 2; ++b) {
                         if (c0 + 32 * b >= a.M) break;
-                        tc::tma_store_3d(&map_cos, tc::smem_u32(sPhi + b * V2_BLK), c0 + 32 * b, row0, chain);
-                        if (rbf) tc::tma_store_3d(&map_sin, tc::smem_u32(sPhi + (2 + b) * V2_BLK), c0 + 32 * b, row0, chain);
+                        tc::tma_store_3d(&map_cos, tc::smem_u32(sPhiT + b * V2_BLK), c0 + 32 * b, row0, chain);
+                        if (rbf) tc::tma_store_3d(&map_sin, tc::smem_u32(sPhiT + (2 + b) * V2_BLK), c0 + 32 * b, row0, chain);
                     }
                     tc::tma_commit();
-                    tc::tma_wait_read0();
+                    if (NPHI == 1) {
+                        tc::tma_wait_read0();
+                        tc::mbar_arrive(phi_empty + pbuf);         // 2 of 2 arrivals: the Phi tile may be overwritten
+                    } else if (t > 0) {
+                        tc::tma_wait_read1();                      // the store of tile t-1 has read its tile; tile t's is in flight
+                        tc::mbar_arrive(phi_empty + ((t - 1) % NPHI));
+                    }
+                } else {
+                    tc::mbar_arrive(phi_empty + pbuf);
                 }
-                tc::mbar_arrive(phi_empty);                // 2 of 2 arrivals: the Phi tile may be overwritten
             }
             tc::tma_wait0();
         }
@@ -629,8 +649,13 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
 template <int NG>
 static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     const int n_kb = (a.d + 31) / 32;
-    const int ns1 = tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1;
-    const size_t smem = tc2_smem_bytes(NG, n_kb, ns1);
+    // DGPRF_TC2_PHI2=1 (A/B experiment): two Phi tiles + a single-stage z ring instead of one Phi tile + two z stages, so that
+    // the store of a tile overlaps the next tile's epilogue.  Measured at configs[4] layer scale: 0.71-0.76 ms against 0.65 ms --
+    // with one z stage GEMM #1 of tile t+1 waits for its 64 KB z tile after GEMM #1 of tile t; the second Phi tile needs the
+    // z ring cut into k-block slots first.
+    const bool phi2 = a.Phi != nullptr && getenv("DGPRF_TC2_PHI2") && tc2_smem_bytes(NG, n_kb, 1) + 4 * (size_t)V2_BLK <= 232448;
+    const int ns1 = phi2 ? 1 : (tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1);
+    const size_t smem = tc2_smem_bytes(NG, n_kb, ns1) + (phi2 ? 4 * (size_t)V2_BLK : 0);
     { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc2<NG, false>, (size_t)232448); if (rc_s) return rc_s; }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
     if (!a.prepped) {
@@ -663,7 +688,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2 | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0), tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2 | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | (phi2 ? 0x200 : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12];

@@ -163,6 +163,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, i
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace tc
