@@ -291,6 +291,11 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(W + ((int64_t)b * y.M + c_lo) * y.g + 32 * i));
         }
     }
+    {   // the targets of this row tile are first needed by the likelihood seed, far down the dependent chain: pull them into L2 now
+        const int ycols = a.likelihood == DGPRF_LIK_GAUSSIAN ? a.d_out : 1;
+        const int nline = (RT * ycols + 31) >> 5;
+        if (tid < nline && row0 < a.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(Y + (int64_t)row0 * ycols + 32 * tid));
+    }
     if (a.x_in_smem)
         for (int e = tid; e < RT * a.d_in; e += kT) {
             const int r = e / a.d_in, q = e - r * a.d_in;

@@ -100,6 +100,9 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     const int NSW = NSW_ & 0xff;
     const bool direct_store = (NSW_ & 0x100) != 0;
     const int NPHI = (NSW_ & 0x200) ? 2 : 1;
+    // NSW_ bit 10 (non-WIDE): the z operand streams through a ring of NS1 k-block slots [hi 8 KB | lo 8 KB] instead of whole
+    // 64 KB tiles, which is what frees the shared memory for the second Phi tile
+    const bool KRING = !WIDE && (NSW_ & 0x400) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* bias_s = reinterpret_cast<float*>(sm);
@@ -108,8 +111,8 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     uint8_t* sW = sPhi + NPHI * 4 * V2_BLK;              // NSW stages x 4 blocks [NG x 32]
     uint8_t* sB1 = sW + NSW * 4 * NG * 128;              // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
                                                          // WIDE: NS1 k-block slots of V2_RING bytes
-    uint64_t* b1_full = bars + 0;     // [3] TMA complete_tx      -> MMA
-    uint64_t* b1_empty = bars + 3;    // [3] MMA commit           -> producer
+    uint64_t* b1_full = bars + 22;    // [6] TMA complete_tx      -> MMA
+    uint64_t* b1_empty = bars + 28;   // [6] MMA commit           -> producer
     uint64_t* d1_full = bars + 6;     // [2] MMA commit           -> epilogue
     uint64_t* d1_empty = bars + 8;    // [2] epilogue warps       -> MMA
     uint64_t* phi_full = bars + 18;   // [2] epilogue warps           -> MMA, store
@@ -136,11 +139,11 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     const int n_my = ct0 < n_ct ? min(per, n_ct - ct0) : 0;
     const int n_kb = (a.d + 31) / 32;
     const int nb2 = rbf ? 4 : 2;
-    const uint32_t b1_stage = WIDE ? (uint32_t)V2_RING : 2u * n_kb * V2_BBLK;
+    const uint32_t b1_stage = WIDE ? (uint32_t)V2_RING : (KRING ? 2u * V2_BBLK : 2u * n_kb * V2_BBLK);
 
     if (warp == V2_EPI_WARPS) tc::tmem_alloc(tmem_slot, V2_TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 6; ++i) {
             tc::mbar_init(b1_full + i, 1);
             tc::mbar_init(b1_empty + i, 1);
         }
@@ -361,6 +364,34 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                 }
                 if (lane == 0) TL(t, 6);
             }
+        } else if (KRING) {
+            // A in tensor memory, z k-blocks from the ring: 12 UMMAs per k-block, the slot is released as soon as they retire
+            int it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int buf = t & 1;
+                tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
+                if (lane == 0) TL(t, 5);
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int slot = it % NS1;
+                    tc::mbar_wait(b1_full + slot, (it / NS1) & 1);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint64_t dzh = dB1 + ((slot * b1_stage) >> 4), dzl = dzh + (V2_BBLK >> 4);
+                        const uint32_t dcol = tm_d1 + 64 * buf;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint32_t acol = 32 * kb + 8 * k4;
+                            tc::umma_tf32_ts(dcol, tm_alo + acol, dzh + 2 * k4, IDESC1, (kb | k4) != 0 ? 1u : 0u);
+                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dzl + 2 * k4, IDESC1, 1u);
+                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dzh + 2 * k4, IDESC1, 1u);
+                        }
+                        tc::umma_commit(b1_empty + slot);              // k-block consumed
+                        if (kb == n_kb - 1) tc::umma_commit(d1_full + buf);   // P ready
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) TL(t, 6);
+            }
         } else
         for (int t = 0; t < n_my; ++t) {
             const int buf = t & 1;
@@ -429,6 +460,16 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                         tc::tma_load_3d(&map_at, sl + V2_BLK, b1_full + slot, 32 * kb, row0, 2 * chain + 1);
                         tc::tma_load_3d(&map_zt, sl + 2 * V2_BLK, b1_full + slot, 32 * kb, c0, 2 * chain);
                         tc::tma_load_3d(&map_zt, sl + 2 * V2_BLK + V2_BBLK, b1_full + slot, 32 * kb, c0, 2 * chain + 1);
+                    }
+                } else if (KRING) {
+                    for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                        const int slot = it % NS1;
+                        tc::mbar_wait(b1_empty + slot, ((it / NS1) & 1) ^ 1);
+                        if (kb == 0) TL(t, 9);
+                        tc::mbar_expect_tx(b1_full + slot, b1_stage);
+                        const uint32_t sl = tc::smem_u32(sB1) + slot * b1_stage;
+                        tc::tma_load_3d(&map_zt, sl, b1_full + slot, 32 * kb, c0, 2 * zc);
+                        tc::tma_load_3d(&map_zt, sl + V2_BBLK, b1_full + slot, 32 * kb, c0, 2 * zc + 1);
                     }
                 } else {
                 // ---- z tile (B of GEMM #1): rows = feature columns, K-major, tf32 hi blocks then lo blocks ----
@@ -654,8 +695,18 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     // with one z stage GEMM #1 of tile t+1 waits for its 64 KB z tile after GEMM #1 of tile t; the second Phi tile needs the
     // z ring cut into k-block slots first.
     const bool phi2 = a.Phi != nullptr && getenv("DGPRF_TC2_PHI2") && tc2_smem_bytes(NG, n_kb, 1) + 4 * (size_t)V2_BLK <= 232448;
-    const int ns1 = phi2 ? 1 : (tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1);
-    const size_t smem = tc2_smem_bytes(NG, n_kb, ns1) + (phi2 ? 4 * (size_t)V2_BLK : 0);
+    // z k-block ring (4 slots of [hi 8 KB | lo 8 KB]) + two Phi tiles when the features are stored and a tile needs at most
+    // three k-blocks (input width <= 96: the ring then has a slot of slack and the store of tile t overlaps the epilogue of
+    // tile t+1 -- 0.62 -> 0.57 ms at B = 65536, d = 90, M = 4096); with four k-blocks per tile it loses to the two whole-tile
+    // stages (0.65 -> 0.69 ms: shared memory has no room for a fifth slot).  DGPRF_TC2_KRING=<slots | 0> overrides.
+    const char* e_kr = getenv("DGPRF_TC2_KRING");
+    int kring = a.Phi == nullptr ? 0 : (e_kr ? atoi(e_kr) : (n_kb <= 3 ? 4 : 0));
+    if (kring > 6) kring = 6;
+    const int nsw_k = getenv("DGPRF_TC2_NSW") ? atoi(getenv("DGPRF_TC2_NSW")) : 2;      // W^T ring stages next to the k-block ring (1 | 2)
+    const size_t smem_kring = 1024 + V2_HDR + 8 * (size_t)V2_BLK + (size_t)(nsw_k == 1 ? 1 : 2) * 4 * (size_t)NG * 128 + (size_t)kring * 2 * V2_BBLK;
+    if (kring < 2 || smem_kring > 232448) kring = 0;
+    const int ns1 = kring ? kring : (phi2 ? 1 : (tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1));
+    const size_t smem = kring ? smem_kring : tc2_smem_bytes(NG, n_kb, ns1) + (phi2 ? 4 * (size_t)V2_BLK : 0);
     { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc2<NG, false>, (size_t)232448); if (rc_s) return rc_s; }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
     if (!a.prepped) {
@@ -688,7 +739,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, 2 | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | (phi2 ? 0x200 : 0), tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12];
