@@ -153,10 +153,8 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         s.CSf = cs0;
         s.tc_cols = 0;
         if (m->precision == DGPRF_PREC_TF32 && (y.M % 4) == 0 && y.g <= 64) {
-            s.tc_cols = dgprf_tc_tile_cols(B, y.M, m->n_chains);
-            const int t = ceil_div(y.M, s.tc_cols);
-            s.CSf = s.tc_cols == 32 ? (t < kMaxSlabs ? t : kMaxSlabs) : cs0;
-            const int c2 = dgprf_fwd_tc2_col_splits(s.tc_cols, B, layer_d(y), y.M, y.g, m->n_chains);
+            // the pipelined tensor-core forward when the layer has enough tiles for it, else the fp32 SIMT kernel
+            const int c2 = dgprf_fwd_tc2_col_splits(dgprf_tc_tile_cols(B, y.M, m->n_chains), B, layer_d(y), y.M, y.g, m->n_chains);
             if (c2 > 0) { s.tc2 = 1; s.CSf = c2; s.tc_cols = 64; }
         }
         s.n_fpart = (int64_t)s.CSf * B * y.g;
@@ -346,7 +344,6 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
             }
             rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);
         }
-        else if (w.L[l].tc_cols != 0 && dgprf_fwd_tc_supported(a)) rc = dgprf_launch_fwd_tc(a, m->n_chains, st);
         else rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
         if (rc) return rc;
     }
@@ -445,7 +442,6 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
             }
             rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
         }
-        else if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc_supported(a)) rc = dgprf_launch_bwd_tc(a, m->n_chains, st);
         else rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
         if (rc) return rc;
         if (hyper) {

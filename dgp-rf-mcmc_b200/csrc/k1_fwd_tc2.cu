@@ -1,6 +1,6 @@
-// K1 v2 (tensor-core, DGPRF_PREC_TF32): warp-specialised, pipelined fused [RF layer -> GP layer] forward (any layer with at
-// least four 128 x 64 tiles; input width <= 128, or any width in the WIDE variant).  Same arithmetic as k1_fwd_tc.cu; what
-// changes is the execution model:
+// K1 (tensor-core, DGPRF_PREC_TF32): warp-specialised, pipelined fused [RF layer -> GP layer] forward (any layer with at
+// least four 128 x 64 tiles; input width <= 128, or any width in the WIDE variant).  Same arithmetic as k1_fwd_simt.cu; the
+// execution model:
 //
 //   * the A operand of GEMM #1, (in * exp(log_inv_ls)) split into tf32 hi + lo, is written ONCE per CTA into
 //     TENSOR MEMORY (tcgen05.st) and consumed from there by every column tile (tcgen05.mma with A in TMEM),
@@ -757,14 +757,21 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
 }
 
 // The pipelined kernel takes 64-column tiles and an input width that fits the TMEM-resident A operand.  Returns the
-// number of column splits (CTAs per row block; each walks M/64/splits column tiles) or 0 when the layered v1
+// number of column splits (CTAs per row block; each walks M/64/splits column tiles) or 0 when the SIMT
 // kernel should run instead: the per-CTA prologue and pipeline fill only pay off over >= 4 tiles per CTA.
+// Tile-width hint for a layer: 32 when 64-wide column tiles would leave most of the 148 SMs without a CTA (small
+// minibatches: the pipelined kernel then runs with as little as one tile per CTA), else 64.
+int dgprf_tc_tile_cols(int B, int M, int n_chains) {
+    const int64_t ctas64 = (int64_t)ceil_div(B, V2_BM) * (ceil_div(M, 64) < kMaxCS ? ceil_div(M, 64) : kMaxCS) * n_chains;
+    return ctas64 < 120 ? 32 : 64;
+}
+
 int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains) {
     if ((M % 4) != 0 || g > 64 || getenv("DGPRF_NO_TC2") != nullptr) return 0;
     const int n_ct = ceil_div(M, V2_BN);
     const int64_t rb = (int64_t)ceil_div(B, V2_BM) * n_chains;
-    // grids too small for the v1 kernel's 64-column tiles (tile_cols == 32) still take this kernel, one tile per CTA if
-    // need be (measured faster from about 4 tiles in total); below that the v1 kernel with 32-column tiles runs
+    // small grids (tile_cols == 32) still take this kernel, one tile per CTA if need be (measured faster than the fp32 SIMT
+    // kernel from about 4 tiles in total); below that the SIMT kernel runs
     if (tile_cols != 64 && (rb * n_ct < 4 || getenv("DGPRF_NO_TC2_SMALL") != nullptr)) return 0;
     int cs = (int)((4 * 148 + rb - 1) / rb);                   // >= 4 waves of CTAs when the problem allows
     if (cs > kMaxCS) cs = kMaxCS;

@@ -1,7 +1,7 @@
-// K2 v2 (tensor-core, DGPRF_PREC_TF32): reverse pass of one [RF layer -> GP layer] pair with every accumulation
-// kept on chip.  Same three UMMAs per (128-row tile, 64-column tile) as k2_bwd_tc.cu,
+// K2 (tensor-core, DGPRF_PREC_TF32): reverse pass of one [RF layer -> GP layer] pair with every accumulation
+// kept on chip.  Three UMMAs per (128-row tile, 64-column tile),
 //   MMA-1  dPhi = dF . W_tile^T      MMA-2  gW_tile += Phi_tile^T . dF      MMA-3  T += dP . z_tile^T
-// but the CTA (row split rs, column split cs) walks its ROW tiles in the outer loop and its column tiles in the
+// and the CTA (row split rs, column split cs) walks its ROW tiles in the outer loop and its column tiles in the
 // inner loop:
 //   * all gW tiles of the CTA's column tiles stay resident in TENSOR MEMORY for the whole kernel (up to 10 tiles of
 //     32 columns) and are written once, as row-split slab rs, at the end;
@@ -14,7 +14,7 @@
 //     kernel because a TMA row stride must be a multiple of 16 bytes; z directly from the model's spectral draws).
 // n_gp <= 32.  W-only mode: d_prev <= 64.  Hyper mode (stochastic-EM / full-Bayes gradients): T is formed for ALL input
 // columns (width <= 128, two passes of 64 z rows through the same z tile), and the raw T and R = rowsum(dP) are written as
-// the partial slabs the hyper reduction (k_hyper_partial / k_hyper_final) consumes.  Other shapes stay on k2_bwd_tc.cu / the
+// the partial slabs the hyper reduction (k_hyper_partial / k_hyper_final) consumes.  Other shapes stay on the fp32
 // SIMT kernel.  Column splits come from a small cost model (dgprf_bwd_tc2_pick_cs); debug: DGPRF_BWD_TIMELINE=<call number>
 // prints per-role clock stamps of one CTA, DGPRF_BWD_PF=<n> adds TMA L2 prefetches n tiles ahead of the ring (no gain measured).
 #include <stdio.h>

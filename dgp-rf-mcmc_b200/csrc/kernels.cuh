@@ -54,7 +54,6 @@ struct PrepArgs { int32_t n_layers; PrepLayer L[DGPRF_MAX_LAYERS]; };
 int dgprf_launch_prep_layers(const PrepArgs& a, int n_chains, cudaStream_t st);
 
 int dgprf_launch_fwd_simt(const FwdArgs& a, int n_chains, cudaStream_t st);
-bool dgprf_fwd_tc_supported(const FwdArgs& a);
 bool dgprf_fwd_tc2_supported(const FwdArgs& a);
 int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_chains);
 int64_t dgprf_fwd_tc2_zt_floats(int M);
@@ -63,14 +62,11 @@ int64_t dgprf_fwd_tc2_ot_floats(int M, int d);
 int64_t dgprf_fwd_tc2_wt_floats(int F, int g);
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
-int dgprf_launch_fwd_tc(const FwdArgs& a, int n_chains, cudaStream_t st);
 bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper);
 int64_t dgprf_bwd_tc2_wp_floats(int F);
 int dgprf_bwd_tc2_pick_cs(int B, int M, int g, int d, int d_prev, int RS, int n_chains, int hyper);
 bool dgprf_bwd_tc2_supported(const BwdArgs& a);
 int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st);
-bool dgprf_bwd_tc_supported(const BwdArgs& a);
-int dgprf_launch_bwd_tc(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_bwd_simt(const BwdArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st);
 int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, int n_chains, cudaStream_t st);

@@ -33,7 +33,7 @@ CASES = {
     "pipelined_rbf_mean": (RegressionDGP, 9, 1, 3, 512, [9, 9, 1], None, True, True, 2048),
     "pipelined_arc_wide": (ClassificationDGP, 100, 10, 2, [512, 320], [28, 10], ["ARC", "RBF"], True, False, 2100),
     # three K blocks of the TMEM-resident A operand (input widths 70 / 110), n_gp = 40 -> 64-column GEMM #2 template,
-    # v1 backward for the wide layer and pipelined backward (d_prev = 40) for the next; ragged last row / column tiles
+    # SIMT backward for the wide layer (n_gp = 40) and pipelined backward (d_prev = 40) for the next; ragged last row / column tiles
     "pipelined_kb3_g40": (RegressionDGP, 70, 3, 2, [708, 516], [40, 3], None, True, True, 1990),
     # two K blocks, arc-cosine through the pipelined backward (zero-filled sin halves), many row tiles per CTA
     "pipelined_arc_kb2": (ClassificationDGP, 50, 5, 3, 512, [12, 20, 5], ["ARC", "ARC", "RBF"], True, False, 4500),
@@ -97,7 +97,7 @@ def test_tc_saved_features_and_gradients(name):
     s0 = e.spec.layers[0]
     Bn = X.shape[0]
     ctas64 = ((Bn + 127) // 128) * min((s0.M + 63) // 64, 8)
-    CS = min((s0.M + 31) // 32, 16) if ctas64 < 120 else min((s0.M + 63) // 64, 8)   # dgprf_tc_tile_cols (v1 kernel)
+    CS = min((s0.M + 63) // 64, 8)                                                       # SIMT forward (col_splits) unless ...
     n_ct, rb = (s0.M + 63) // 64, (Bn + 127) // 128                                    # dgprf_fwd_tc2_col_splits
     if ctas64 >= 120 or rb * n_ct >= 4:
         c2 = max(1, min((4 * 148 + rb - 1) // rb, 8, n_ct))
@@ -159,7 +159,10 @@ def test_pipelined_cases_run_the_pipelined_kernels(name):
     names = [nm for nm, _ in _ffi.profile_stop()]
     assert ("k1_fwd_tc2_wide" if name == "pipelined_wide" else "k1_fwd_tc2") in names, names
     assert "k2_bwd_tc2" in names, names
-    assert "k1_fwd_simt" not in names and "k2_bwd_simt" not in names, names
+    assert "k1_fwd_simt" not in names, names
+    # the pipelined backward takes n_gp <= 32; a wider GP layer (the 40-wide one of pipelined_kb3_g40) runs its backward on
+    # the fp32 SIMT kernel, the other layers of the model still on the tensor cores
+    assert ("k2_bwd_simt" in names) == (max(CASES[name][5]) > 32), names
 
 
 @pytest.mark.parametrize("name", ["pipelined_rbf_mean", "pipelined_arc_wide", "pipelined_kb3_g40", "protein_full_layer",
