@@ -435,6 +435,20 @@ def run_ours(args, rank, world):
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": None, "kernel": dom["kernel"], "avg_us": dom["avg_us"], "peak_source": pk_src}
 
+    # ---- the per-sample cost besides the cycle of steps: the evaluation forward over the test split (10 % of N) -------------
+    n_test = N // 10
+    Xe, Ye = X[:n_test].contiguous(), Y[:n_test].contiguous()
+    for _ in range(3):
+        model.eval_log_likelihood_and_se([(Xe, Ye)])
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s0.record(stream)
+    for _ in range(10):
+        model.eval_log_likelihood_and_se([(Xe, Ye)])
+    s1.record(stream)
+    torch.cuda.synchronize()
+    eval_ms = s0.elapsed_time(s1) / 10
+
     # ---- one epoch of sampling steps as ONE CUDA-graph launch (the sampler drivers' graph=True mode) ----------
     from experiments.utils_dataset import DeviceDataset
     from experiments.utils_training import EpochGraph
@@ -539,8 +553,9 @@ def run_ours(args, rank, world):
         "timing": "value: per-step CUDA events on the launch stream, L2 flushed between timed steps (256 MiB write), the launch queue primed "
                   "behind a 1 ms device-side sleep so that host launch jitter is not counted as device time; max over ranks",
         "precision": prec_note, "parallelism": f"{world} independent chain(s), 1 per GPU, no data-path collective",
-        "posterior_samples_per_second": it_s / (50 * nb),
-        "samples_note": f"cycle = 50 epochs x {nb} it (SURVEY 8d); excludes the per-sample test-set eval",
+        "posterior_samples_per_second": world / (50 * nb * (t_dev / K) + eval_ms * 1e-3),
+        "samples_note": f"one posterior sample = a cycle of 50 epochs x {nb} it (SURVEY 8d) + the evaluation forward over the {n_test}-point "
+                        f"test split ({eval_ms:.3f} ms, models/regression_model.py:33-50)",
         "graph_epoch": graph_epoch,
         "warm_loop": {"value": world * K / t_warm, "unit": UNIT, "note": "back-to-back steps, no L2 flush, CPU launch cost included"},
         "e2e": {"value": world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * B * (CFG["D"] + 1), "d2h_bytes_per_step": 4,

@@ -26,6 +26,10 @@
 #include "kernels.cuh"
 #include "update_core.cuh"
 
+#ifndef K10_VAR
+#define K10_VAR 0
+#endif
+
 namespace {
 
 constexpr int kT = 512;          // threads per CTA
@@ -167,15 +171,15 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
 // columns).  Warp partials -> `red`, fixed-order sum over the warps = this CTA's partial, pushed to every CTA of the
 // cluster; then every CTA sums the CL partials in rank order (deterministic, identical on all CTAs) and hands element
 // (r, c) to `consume` on the thread that owns it.  The caller synchronises the CTA after its own follow-up work.
-template <int MT, typename Consume>
-__device__ __forceinline__ void reduce_gather(const float (&acc)[MT][kNJ][4], int nt, Xchg& x, Consume&& consume) {
+template <int MT, int NJM, typename Consume>
+__device__ __forceinline__ void reduce_gather(const float (&acc)[MT][NJM][4], int nt, Xchg& x, Consume&& consume) {
     constexpr int RT = 16 * MT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ncs = x.ncs, CL = x.CL;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int j = 0; j < kNJ; ++j)
+        for (int j = 0; j < NJM; ++j)
             if (j < nt) {
                 float* p = x.red + ((warp * RT + mt * 16 + g) * ncs + j * 8 + 2 * t);
                 *reinterpret_cast<float2*>(p) = make_float2(acc[mt][j][0], acc[mt][j][1]);
@@ -228,7 +232,10 @@ __device__ __forceinline__ void reduce_gather(const float (&acc)[MT][kNJ][4], in
     ++x.n;
 }
 
-template <int MT>
+// NJM: most 8-wide tiles of any GP output / previous-layer width of the model (1 | 2 | 4): every loop over those tiles is
+// unrolled to NJM with warp-uniform guards, and the unrolled-but-skipped iterations are not free (code size, guards):
+// configs[1] (n_gp = 9 -> two tiles) runs 8 % faster with NJM = 2 than with 4.
+template <int MT, int NJM>
 __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant__ ClArgs a, const __grid_constant__ SegTable tab) {
     constexpr int RT = 16 * MT;
     constexpr int LDT = RT + 4;                          // row stride of the transposed dF operand
@@ -357,15 +364,20 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
         const float* z = y.z + chain * y.z_cs;
         const float* W = y.W + chain * a.w_cs;
+        // keep the two base pointers in registers: under the 128-register cap ptxas otherwise re-derives chain * stride +
+        // base (64-bit multiplies and carries) in front of EVERY operand load of the chain
+#if (K10_VAR & 1)
+        asm volatile("" : "+l"(z), "+l"(W));
+#endif
         const float scale = (rbf ? 1.f : 1.41421356237f) * __expf(__ldg(y.log_amp + chain * a.h_cs)) * rsqrtf((float)M);
         float* phi = phi_all + y.phi_off;
         const int NJ = (G + 7) >> 3;
         const int nblk = rbf ? 2 : 1;
-        float facc[MT][kNJ][4];
+        float facc[MT][NJM][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < kNJ; ++j)
+            for (int j = 0; j < NJM; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) facc[mt][j][i] = 0.f;
 
@@ -375,13 +387,31 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             // K slot t <-> feature f0 = n0 + 2t, slot t+4 <-> f0 + 1;  n <-> output column j = 8 jt + g
             // Out-of-range rows / columns are CLAMPED instead of predicated: a clamped W column only feeds output columns
             // >= G (never read), a clamped feature row meets Phi = 0.
-            float wv[2][kNJ][2];
+            float wv[2][NJM][2];
+#if (K10_VAR & 2)
+            // The loads are unconditional (clamped indices instead of `if (j < NJ)`): a warp-uniform condition the compiler
+            // cannot prove uniform costs a BSSY / BSYNC / BRA region around every pair of loads.
+            {
+                const int f0 = min(n0 + 2 * t, c_hi - 1), f1 = min(n0 + 2 * t + 1, c_hi - 1);
+                const int sb = rbf ? M * G : 0;                          // arc-cosine: block 1 is never used, re-read block 0
+                const float* w0 = W + f0 * G;
+                const float* w1 = W + f1 * G;
+#pragma unroll
+                for (int j = 0; j < NJM; ++j) {
+                    const int jj = min(j * 8 + g, G - 1);
+                    wv[0][j][0] = __ldg(w0 + jj);
+                    wv[0][j][1] = __ldg(w1 + jj);
+                    wv[1][j][0] = __ldg(w0 + sb + jj);
+                    wv[1][j][1] = __ldg(w1 + sb + jj);
+                }
+            }
+#else
             {
                 const int f0 = min(n0 + 2 * t, c_hi - 1), f1 = min(n0 + 2 * t + 1, c_hi - 1);
 #pragma unroll
                 for (int b = 0; b < 2; ++b)
 #pragma unroll
-                    for (int j = 0; j < kNJ; ++j) {
+                    for (int j = 0; j < NJM; ++j) {
                         wv[b][j][0] = wv[b][j][1] = 0.f;
                         if (b < nblk && j < NJ) {
                             const int jj = min(j * 8 + g, G - 1);
@@ -390,6 +420,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                         }
                     }
             }
+#endif
             // ---- GEMM #1: P tile [RT x 8] = A [RT x Kp] . z[:, n0:n0+8]
             float acc[MT][4];
 #pragma unroll
@@ -465,7 +496,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                         else acc_to_a(w[mt], ah[mt], al[mt]);
                     }
 #pragma unroll
-                    for (int j = 0; j < kNJ; ++j)
+                    for (int j = 0; j < NJM; ++j)
                         if (j < NJ) {
                             uint32_t bh0, bl0, bh1, bl1;
                             split_tf32(wv[b][j][0], bh0, bl0);
@@ -479,7 +510,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         {   // F_l = sum of the partials; the owner of element (r, c) also writes the next layer's A operand
             const bool more = l + 1 < L;
             const float* s_n = s_all + (more ? l + 1 : l) * a.dmax;
-            reduce_gather<MT>(facc, NJ, xc, [&](int r, int c, float v) {
+            reduce_gather<MT, NJM>(facc, NJ, xc, [&](int r, int c, float v) {
                 f_s[r * kFS + c] = v;
                 if (more && c < G) {
                     uint32_t hi, lo;
@@ -581,16 +612,19 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
         const float* z = y.z + chain * y.z_cs;
         const float* W = y.W + chain * a.w_cs;
+#if (K10_VAR & 1)
+        asm volatile("" : "+l"(z), "+l"(W));
+#endif
         const float* phi = phi_all + y.phi_off;
         float* gw = a.gwpart + chain * a.gw_cs + (int64_t)tile * a.gw_ss + y.off_W;
         const float arc_scale = 1.41421356237f * __expf(__ldg(y.log_amp + chain * a.h_cs)) * rsqrtf((float)M);
         const int nq_cols = y.d_prev + (y.has_mean ? 1 : 0);      // T columns (+ the row-sum column)
         const int NQ = l > 0 ? (nq_cols + 7) >> 3 : 0;
-        float tacc[MT][kNJ][4];
+        float tacc[MT][NJM][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < kNJ; ++j)
+            for (int j = 0; j < NJM; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) tacc[mt][j][i] = 0.f;
 
@@ -599,9 +633,9 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             const int lc = n0 - c_lo;
             if (l > 0) {
                 // z fragments of the T GEMM, requested first: K slot t <-> column n0 + 2t, slot t+4 <-> n0 + 2t + 1; n <-> q
-                float zv[kNJ][2];
+                float zv[NJM][2];
 #pragma unroll
-                for (int j = 0; j < kNJ; ++j) {
+                for (int j = 0; j < NJM; ++j) {
                     const int q = j * 8 + g, c0 = n0 + 2 * t;
                     float b0 = 0.f, b1 = 0.f;
                     if (j < NQ) {                             // clamped row / column: dP is zero beyond c_hi, T columns >= d_prev are never read
@@ -622,7 +656,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                         for (int i = 0; i < 4; ++i) dacc[b][mt][i] = 0.f;
                 const int fcl = min(n0 + g, c_hi - 1);        // clamped feature row of W: its dP is zero (Phi = 0 there)
 #pragma unroll
-                for (int j = 0; j < kNJ; ++j)
+                for (int j = 0; j < NJM; ++j)
                     if (j < NJ) {
                         uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
@@ -671,7 +705,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                     uint32_t ah[4], al[4];
                     acc_to_a(dp, ah, al);
 #pragma unroll
-                    for (int j = 0; j < kNJ; ++j)
+                    for (int j = 0; j < NJM; ++j)
                         if (j < NQ) {
                             uint32_t bh0, bl0, bh1, bl1;
                             split_tf32(zv[j][0], bh0, bl0);
@@ -685,9 +719,9 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
 #pragma unroll
             for (int b = 0; b < 2; ++b)
                 if (b < nblk) {
-                    float gacc[2][4];
+                    float gacc[(NJM + 1) / 2][4];
 #pragma unroll
-                    for (int mj = 0; mj < 2; ++mj)
+                    for (int mj = 0; mj < (NJM + 1) / 2; ++mj)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) gacc[mj][i] = 0.f;
 #pragma unroll
@@ -697,7 +731,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                         split_tf32(pb[0], bh0, bl0);
                         split_tf32(pb[4 * y.ldp], bh1, bl1);
 #pragma unroll
-                        for (int mj = 0; mj < 2; ++mj)
+                        for (int mj = 0; mj < (NJM + 1) / 2; ++mj)
                             if (mj < MJ) {
                                 const float* ph = t_hi + (mj * 16 + g) * LDT + kr * 8 + t;
                                 const float* pl = t_lo + (mj * 16 + g) * LDT + kr * 8 + t;
@@ -710,7 +744,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                             }
                     }
 #pragma unroll
-                    for (int mj = 0; mj < 2; ++mj)
+                    for (int mj = 0; mj < (NJM + 1) / 2; ++mj)
                         if (mj < MJ) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -728,7 +762,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             const int Gp = yp.g, NJp = (Gp + 7) >> 3, MJp = (Gp + 15) >> 4;
             const float* s_l = s_all + l * a.dmax;
             const bool direct = !y.has_mean;
-            reduce_gather<MT>(tacc, NQ, xc, [&](int r, int c, float v) {
+            reduce_gather<MT, NJM>(tacc, NQ, xc, [&](int r, int c, float v) {
                 if (direct) put_dF(r, c, c < Gp ? v * s_l[c] : 0.f, NJp, MJp);
                 else f_s[r * kFS + c] = v;
             });
@@ -839,10 +873,10 @@ bool make_plan(const dgprf_model* m, int B, ClPlan* p) {
     int Mmax = 1;
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
-        if (y.g > 32 || y.d_prev + (y.has_mean ? 1 : 0) > 32 || y.d_prev + y.d_x > 1024) return false;
+        if (y.g > 8 * kNJ || y.d_prev + (y.has_mean ? 1 : 0) > 8 * kNJ || y.d_prev + y.d_x > 1024) return false;
         if (y.M > Mmax) Mmax = y.M;
     }
-    if (m->d_out > 32) return false;
+    if (m->d_out > 8 * kNJ) return false;
     const char* e_mt = getenv("DGPRF_K10_MT");
     const char* e_cl = getenv("DGPRF_K10_CL");
     static const int cap[9] = {0, 148, 148, 0, 128, 0, 0, 0, 112};     // co-resident CTAs per cluster size (1 CTA / SM)
@@ -884,12 +918,12 @@ int dgprf_step_cluster_tiles(const dgprf_model* m, int B) {
     return make_plan(m, B, &p) ? p.n_tiles : 0;
 }
 
-template <int MT>
-static int ensure_smem(size_t smem) { return dgprf_ensure_smem((const void*)k10_step_cluster<MT>, smem); }
+template <int MT, int NJM>
+static int ensure_smem(size_t smem) { return dgprf_ensure_smem((const void*)k10_step_cluster<MT, NJM>, smem); }
 
-template <int MT>
+template <int MT, int NJM>
 static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
-    const int rc0 = ensure_smem<MT>(smem);
+    const int rc0 = ensure_smem<MT, NJM>(smem);
     if (rc0) return rc0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -907,7 +941,7 @@ static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t sme
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k10_step_cluster<MT>, a, tab);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k10_step_cluster<MT, NJM>, a, tab);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         dgprf_set_error("k10_step_cluster launch failed: %s (grid %u x %u, cluster %d, smem %zu, cooperative %d)",
@@ -920,9 +954,9 @@ static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t sme
 static int g_dbg_calls = 0;
 static int dbg_calls_peek() { return g_dbg_calls; }
 
-template <int MT>
+template <int MT, int NJM>
 static int max_coresident(int CL, size_t smem) {
-    if (ensure_smem<MT>(smem) != DGPRF_OK) return 0;
+    if (ensure_smem<MT, NJM>(smem) != DGPRF_OK) return 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem;
@@ -931,11 +965,26 @@ static int max_coresident(int CL, size_t smem) {
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k10_step_cluster<MT>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, k10_step_cluster<MT, NJM>, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
     return n * CL;
+}
+
+// (MT, NJM) -> instantiation
+static int launch_any(int MT, int NJM, const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
+#define K10_CASE(mt, nj) if (MT == mt && NJM == nj) return launch_cl<mt, nj>(a, tab, grid, smem, coop, st);
+    K10_CASE(1, 1) K10_CASE(1, 2) K10_CASE(1, 4) K10_CASE(2, 1) K10_CASE(2, 2) K10_CASE(2, 4)
+#undef K10_CASE
+    dgprf_set_error("k10: no instantiation for MT=%d NJM=%d", MT, NJM);
+    return DGPRF_EINVAL;
+}
+static int coresident_any(int MT, int NJM, int CL, size_t smem) {
+#define K10_CASE(mt, nj) if (MT == mt && NJM == nj) return max_coresident<mt, nj>(CL, smem);
+    K10_CASE(1, 1) K10_CASE(1, 2) K10_CASE(1, 4) K10_CASE(2, 1) K10_CASE(2, 2) K10_CASE(2, 4)
+#undef K10_CASE
+    return 0;
 }
 
 // Same contract as dgprf_launch_step_rows: upd != nullptr asks for the fused update, *fused reports whether it ran.
@@ -956,6 +1005,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     int lda = 0, dmax = 0, ncs = 0;
     const size_t smem = plan_smem(m, p.MT, p.CL, &lda, &dmax, &ncs);
     a.lda = lda; a.dmax = dmax; a.ncs = ncs; a.x_in_smem = x_staged(m, p.MT) ? 1 : 0;
+    const int NJM = ncs <= 8 ? 1 : (ncs <= 16 ? 2 : 4);          // ncs = 8 x the most tiles any exchanged matrix of the model has
     int64_t phis = 0;
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
@@ -978,15 +1028,15 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     static const bool under_ncu = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
                                   getenv("NV_NSIGHT_INJECTION_PORT_BASE");
     if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE") && !(under_ncu && p.CL > 1)) {
-        static int cached[16][3][9];                     // [device][MT][CL] -> co-resident CTAs + 1 (0: not yet queried) ...
-        static size_t cached_smem[16][3][9];             // ... for this shared-memory size
+        static int cached[16][3][5][9];                  // [device][MT][NJM][CL] -> co-resident CTAs + 1 (0: not yet queried) ...
+        static size_t cached_smem[16][3][5][9];          // ... for this shared-memory size
         int dev = 0;
         DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
         int cap = 0;
-        if (dev < 16 && cached[dev][p.MT][p.CL] > 0 && cached_smem[dev][p.MT][p.CL] == smem) cap = cached[dev][p.MT][p.CL] - 1;
+        if (dev < 16 && cached[dev][p.MT][NJM][p.CL] > 0 && cached_smem[dev][p.MT][NJM][p.CL] == smem) cap = cached[dev][p.MT][NJM][p.CL] - 1;
         else {
-            cap = p.MT == 2 ? max_coresident<2>(p.CL, smem) : max_coresident<1>(p.CL, smem);
-            if (dev < 16) { cached[dev][p.MT][p.CL] = cap + 1; cached_smem[dev][p.MT][p.CL] = smem; }
+            cap = coresident_any(p.MT, NJM, p.CL, smem);
+            if (dev < 16) { cached[dev][p.MT][NJM][p.CL] = cap + 1; cached_smem[dev][p.MT][NJM][p.CL] = smem; }
         }
         if (getenv("DGPRF_K10_TIMING") && dbg_calls_peek() == 0)
             fprintf(stderr, "k10: MT %d CL %d grid %u x %u smem %zu co-resident cap %d\n", p.MT, p.CL, grid.x, grid.y, smem, cap);
@@ -1005,12 +1055,12 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     int rc;
     {
         ProfScope _ps("k10_step_cluster", st);
-        rc = p.MT == 2 ? launch_cl<2>(a, tab, grid, smem, a.fuse_update != 0, st) : launch_cl<1>(a, tab, grid, smem, a.fuse_update != 0, st);
+        rc = launch_any(p.MT, NJM, a, tab, grid, smem, a.fuse_update != 0, st);
         if (rc != DGPRF_OK && a.fuse_update) {           // cooperative + cluster launch refused: run unfused, K5 follows
             if (getenv("DGPRF_K10_TIMING")) fprintf(stderr, "k10: fused launch refused: %s\n", dgprf_last_error());
             a.fuse_update = 0;
             *fused = false;
-            rc = p.MT == 2 ? launch_cl<2>(a, tab, grid, smem, false, st) : launch_cl<1>(a, tab, grid, smem, false, st);
+            rc = launch_any(p.MT, NJM, a, tab, grid, smem, false, st);
         }
     }
     if (rc) return rc;
@@ -1020,7 +1070,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         const int n = 5 * m->n_layers + 2 + (a.fuse_update ? 2 : 0);      // stamps: start, setup, 2 per forward layer, seed, 3 per backward layer (-1), update
-        fprintf(stderr, "k10 (MT %d, CL %d, grid %u) phase cycles:", p.MT, p.CL, grid.x);
+        fprintf(stderr, "k10 (MT %d, NJM %d, CL %d, grid %u) phase cycles:", p.MT, NJM, p.CL, grid.x);
         for (int i = 1; i < n; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
         fprintf(stderr, "  total %lld\n", h[n - 1] - h[0]);
     }

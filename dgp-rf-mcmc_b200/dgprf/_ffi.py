@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdgprf.so")
+LIB_PATH = os.environ.get("DGPRF_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libdgprf.so")   # override: A/B builds
 
 MAX_LAYERS = 8
 MAX_SEGMENTS = 64
