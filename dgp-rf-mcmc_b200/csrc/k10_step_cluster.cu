@@ -235,7 +235,9 @@ __device__ __forceinline__ void reduce_gather(const float (&acc)[MT][NJM][4], in
 // NJM: most 8-wide tiles of any GP output / previous-layer width of the model (1 | 2 | 4): every loop over those tiles is
 // unrolled to NJM with warp-uniform guards, and the unrolled-but-skipped iterations are not free (code size, guards):
 // configs[1] (n_gp = 9 -> two tiles) runs 8 % faster with NJM = 2 than with 4.
-template <int MT, int NJM>
+// KIND: 0 every layer RBF, 1 every layer arc-cosine, 2 mixed (decided per layer at run time): the feature-map branches of
+// the epilogue, the second (sine) block of GEMM #2 / dPhi / gW and the dP formula become compile-time.
+template <int MT, int NJM, int KIND>
 __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant__ ClArgs a, const __grid_constant__ SegTable tab) {
     constexpr int RT = 16 * MT;
     constexpr int LDT = RT + 4;                          // row stride of the transposed dF operand
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     for (int l = 0; l < L; ++l) {
         const ClLayer& y = a.layer[l];
         const int d = y.d_prev + y.d_x, M = y.M, G = y.g;
-        const bool rbf = y.kind == DGPRF_KIND_RBF;
+        const bool rbf = KIND == 0 ? true : (KIND == 1 ? false : y.kind == DGPRF_KIND_RBF);
         const int Kp = (d + 7) & ~7;
         const int c_lo = rank * y.cols, c_hi = min(M, c_lo + y.cols);
         const int ntile = c_hi > c_lo ? (c_hi - c_lo + 7) >> 3 : 0;
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     for (int l = L - 1; l >= 0; --l) {
         const ClLayer& y = a.layer[l];
         const int M = y.M, G = y.g;
-        const bool rbf = y.kind == DGPRF_KIND_RBF;
+        const bool rbf = KIND == 0 ? true : (KIND == 1 ? false : y.kind == DGPRF_KIND_RBF);
         const int NJ = (G + 7) >> 3, MJ = (G + 15) >> 4;
         const int nblk = rbf ? 2 : 1;
         // ---- dF_l operands (a_hi / a_lo: A of dPhi = dF W^T; t_hi / t_lo: dF^T, A of gW^T = dF^T Phi).  The top layer's
@@ -918,12 +920,12 @@ int dgprf_step_cluster_tiles(const dgprf_model* m, int B) {
     return make_plan(m, B, &p) ? p.n_tiles : 0;
 }
 
-template <int MT, int NJM>
-static int ensure_smem(size_t smem) { return dgprf_ensure_smem((const void*)k10_step_cluster<MT, NJM>, smem); }
+template <int MT, int NJM, int KIND>
+static int ensure_smem(size_t smem) { return dgprf_ensure_smem((const void*)k10_step_cluster<MT, NJM, KIND>, smem); }
 
-template <int MT, int NJM>
+template <int MT, int NJM, int KIND>
 static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
-    const int rc0 = ensure_smem<MT, NJM>(smem);
+    const int rc0 = ensure_smem<MT, NJM, KIND>(smem);
     if (rc0) return rc0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -941,7 +943,7 @@ static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t sme
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k10_step_cluster<MT, NJM>, a, tab);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k10_step_cluster<MT, NJM, KIND>, a, tab);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         dgprf_set_error("k10_step_cluster launch failed: %s (grid %u x %u, cluster %d, smem %zu, cooperative %d)",
@@ -954,9 +956,9 @@ static int launch_cl(const ClArgs& a, const SegTable& tab, dim3 grid, size_t sme
 static int g_dbg_calls = 0;
 static int dbg_calls_peek() { return g_dbg_calls; }
 
-template <int MT, int NJM>
+template <int MT, int NJM, int KIND>
 static int max_coresident(int CL, size_t smem) {
-    if (ensure_smem<MT, NJM>(smem) != DGPRF_OK) return 0;
+    if (ensure_smem<MT, NJM, KIND>(smem) != DGPRF_OK) return 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem;
@@ -965,24 +967,27 @@ static int max_coresident(int CL, size_t smem) {
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k10_step_cluster<MT, NJM>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, k10_step_cluster<MT, NJM, KIND>, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
     return n * CL;
 }
 
-// (MT, NJM) -> instantiation
-static int launch_any(int MT, int NJM, const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
-#define K10_CASE(mt, nj) if (MT == mt && NJM == nj) return launch_cl<mt, nj>(a, tab, grid, smem, coop, st);
-    K10_CASE(1, 1) K10_CASE(1, 2) K10_CASE(1, 4) K10_CASE(2, 1) K10_CASE(2, 2) K10_CASE(2, 4)
+// (MT, NJM, KIND) -> instantiation
+#define K10_ALL(X) X(1, 1, 0) X(1, 2, 0) X(1, 4, 0) X(2, 1, 0) X(2, 2, 0) X(2, 4, 0) \
+                   X(1, 1, 1) X(1, 2, 1) X(1, 4, 1) X(2, 1, 1) X(2, 2, 1) X(2, 4, 1) \
+                   X(1, 1, 2) X(1, 2, 2) X(1, 4, 2) X(2, 1, 2) X(2, 2, 2) X(2, 4, 2)
+static int launch_any(int MT, int NJM, int KIND, const ClArgs& a, const SegTable& tab, dim3 grid, size_t smem, bool coop, cudaStream_t st) {
+#define K10_CASE(mt, nj, kd) if (MT == mt && NJM == nj && KIND == kd) return launch_cl<mt, nj, kd>(a, tab, grid, smem, coop, st);
+    K10_ALL(K10_CASE)
 #undef K10_CASE
-    dgprf_set_error("k10: no instantiation for MT=%d NJM=%d", MT, NJM);
+    dgprf_set_error("k10: no instantiation for MT=%d NJM=%d KIND=%d", MT, NJM, KIND);
     return DGPRF_EINVAL;
 }
-static int coresident_any(int MT, int NJM, int CL, size_t smem) {
-#define K10_CASE(mt, nj) if (MT == mt && NJM == nj) return max_coresident<mt, nj>(CL, smem);
-    K10_CASE(1, 1) K10_CASE(1, 2) K10_CASE(1, 4) K10_CASE(2, 1) K10_CASE(2, 2) K10_CASE(2, 4)
+static int coresident_any(int MT, int NJM, int KIND, int CL, size_t smem) {
+#define K10_CASE(mt, nj, kd) if (MT == mt && NJM == nj && KIND == kd) return max_coresident<mt, nj, kd>(CL, smem);
+    K10_ALL(K10_CASE)
 #undef K10_CASE
     return 0;
 }
@@ -1006,6 +1011,9 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     const size_t smem = plan_smem(m, p.MT, p.CL, &lda, &dmax, &ncs);
     a.lda = lda; a.dmax = dmax; a.ncs = ncs; a.x_in_smem = x_staged(m, p.MT) ? 1 : 0;
     const int NJM = ncs <= 8 ? 1 : (ncs <= 16 ? 2 : 4);          // ncs = 8 x the most tiles any exchanged matrix of the model has
+    int n_rbf = 0;
+    for (int l = 0; l < m->n_layers; ++l) n_rbf += m->layer[l].kind == DGPRF_KIND_RBF ? 1 : 0;
+    const int KIND = n_rbf == m->n_layers ? 0 : (n_rbf == 0 ? 1 : 2);
     int64_t phis = 0;
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
@@ -1028,14 +1036,14 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     static const bool under_ncu = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
                                   getenv("NV_NSIGHT_INJECTION_PORT_BASE");
     if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE") && !(under_ncu && p.CL > 1)) {
-        static int cached[16][3][5][9];                  // [device][MT][NJM][CL] -> co-resident CTAs + 1 (0: not yet queried) ...
+        static int cached[16][3][5][9];                  // [device][MT][NJM][CL] (the feature-map kind does not change the resources) -> co-resident CTAs + 1 (0: not yet queried) ...
         static size_t cached_smem[16][3][5][9];          // ... for this shared-memory size
         int dev = 0;
         DGPRF_CHECK_CUDA(cudaGetDevice(&dev));
         int cap = 0;
         if (dev < 16 && cached[dev][p.MT][NJM][p.CL] > 0 && cached_smem[dev][p.MT][NJM][p.CL] == smem) cap = cached[dev][p.MT][NJM][p.CL] - 1;
         else {
-            cap = coresident_any(p.MT, NJM, p.CL, smem);
+            cap = coresident_any(p.MT, NJM, KIND, p.CL, smem);
             if (dev < 16) { cached[dev][p.MT][NJM][p.CL] = cap + 1; cached_smem[dev][p.MT][NJM][p.CL] = smem; }
         }
         if (getenv("DGPRF_K10_TIMING") && dbg_calls_peek() == 0)
@@ -1055,12 +1063,12 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     int rc;
     {
         ProfScope _ps("k10_step_cluster", st);
-        rc = launch_any(p.MT, NJM, a, tab, grid, smem, a.fuse_update != 0, st);
+        rc = launch_any(p.MT, NJM, KIND, a, tab, grid, smem, a.fuse_update != 0, st);
         if (rc != DGPRF_OK && a.fuse_update) {           // cooperative + cluster launch refused: run unfused, K5 follows
             if (getenv("DGPRF_K10_TIMING")) fprintf(stderr, "k10: fused launch refused: %s\n", dgprf_last_error());
             a.fuse_update = 0;
             *fused = false;
-            rc = launch_any(p.MT, NJM, a, tab, grid, smem, false, st);
+            rc = launch_any(p.MT, NJM, KIND, a, tab, grid, smem, false, st);
         }
     }
     if (rc) return rc;
