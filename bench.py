@@ -152,7 +152,7 @@ def algorithmic_flops(spec, B):
 
 
 # ncu --set full captures of the dominant kernel on THIS workload (profiles/r02_ncu_summary.md): DRAM bytes per launch
-NCU_TRAFFIC = {"k10_": (300544.0, "profiles/r02_ncu_k10_raw.csv"), "k9_": (408576.0, "profiles/r01_ncu_full_summary.md section E")}
+NCU_TRAFFIC = {"k10_": (290048.0, "profiles/r02_ncu_k10_raw.csv"), "k9_": (408576.0, "profiles/r01_ncu_full_summary.md section E")}
 
 CFG4 = dict(workload="configs[3]: 3-layer RBF RF-DGP on the synthetic YearPrediction shape, 8 chains per GPU batched per launch, "
                      "sharded predictive averaging", N=515345, D=90, L=3, n_rf=512, n_gp=[30, 30, 1], input_cat=True,
@@ -427,8 +427,8 @@ def run_ours(args, rank, world):
                 "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
                 "peak_source": "cuBLAS TF32 matmul 8192^3 measured live in this run (best of 10)",
                 "binding_resource": "issue slots / dependent-phase latency, NOT the tensor pipe: configs[1] is 0.18 GFLOP and 0.4 MB of "
-                                    "parameters per step; ncu (profiles/r02_ncu_summary.md): tensor pipe ~10 % active (legacy mma.sync tf32 "
-                                    "measures 1024 FLOP/clk/SM on B200, a third of that with the 3xTF32 split), issue slots 39 %, 16 warps/SM",
+                                    "parameters per step; ncu (profiles/r02_ncu_summary.md): tensor pipe 13 % active (legacy mma.sync tf32 "
+                                    "measures 1024 FLOP/clk/SM on B200, a third of that with the 3xTF32 split), issue slots 46 %, 16 warps/SM",
                 "note": "roofline_tc_layer and roofline_k5_256MiB in this line give the tcgen05 and update kernels at throughput-relevant sizes"}
     else:
         ach = dom["bytes"] / (dom["avg_us"] * 1e-6) / 1e9
