@@ -1,0 +1,3 @@
+// K10 instantiations for clusters of 4 CTAs (see k10_step_cluster.cuh)
+#include "k10_step_cluster.cuh"
+K10_DEFINE_CL(4)

@@ -1,5 +1,12 @@
-"""In-tree build of libdgprf.so with nvcc for sm_100a (no JIT cache, no torch extension)."""
+"""In-tree build of libdgprf.so with nvcc for sm_100a (no JIT cache, no torch extension).
+
+Every .cu under csrc/ is compiled to an object in parallel (the template instantiations of the largest kernel are spread
+over several translation units for that reason: `nvcc --split-compile` was tried instead and produced slower code -- the
+fused update of K10 went from 3.5 k to 8.3 k cycles) and the objects are linked into lib/libdgprf.so; objects are rebuilt only
+when their source, a header or the flags changed."""
+import concurrent.futures
 import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -7,35 +14,61 @@ import subprocess
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
+OBJ_DIR = os.path.join(_PKG, "build", "obj")
 LIB = os.path.join(LIB_DIR, "libdgprf.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(_PKG), "include", "dgprf.h")]
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        [os.path.join(os.path.dirname(_PKG), "include", "dgprf.h")]
-    return any(os.path.getmtime(p) > t for p in deps)
+    return any(os.path.getmtime(p) > t for p in sources() + _headers())
+
+
+def _compile(nvcc, src, obj, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n" + r.stdout + r.stderr)
+    return r.stderr
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into lib/libdgprf.so.  Returns the library path."""
+    """Compile every .cu under csrc/ and link lib/libdgprf.so.  Returns the library path."""
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    tag = hashlib.sha1(" ".join(NVCC_FLAGS).encode()).hexdigest()[:8]
+    newest_header = max(os.path.getmtime(p) for p in _headers())
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ_DIR, f"{os.path.splitext(os.path.basename(src))[0]}.{tag}.o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append((src, obj))
+    live = set(objs)
+    for stale in glob.glob(os.path.join(OBJ_DIR, "*.o")):            # objects of deleted / renamed sources
+        if stale not in live:
+            os.remove(stale)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, max(1, len(jobs)))) as pool:
+        logs = list(pool.map(lambda j: _compile(nvcc, j[0], j[1], verbose), jobs))
     if verbose:
-        print(r.stderr)
+        print("".join(logs))
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     return LIB
