@@ -90,19 +90,20 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Same self-resetting grid barrier as K9 (cooperative launch: all CTAs co-resident; bounded spin).
-__device__ __forceinline__ void grid_barrier_cl(unsigned int* bar, unsigned int my_gen, unsigned int n_ctas) {
+// Grid-wide barrier for the cooperative launch (all CTAs co-resident), ONE atomic per CTA: `ticket` only ever grows, a CTA
+// that draws ticket t waits until the counter reaches the end of t's round, (t / n + 1) * n -- the last arriver's own atomic
+// is the release, there is no second "generation" word to bump (one L2 round trip less on the critical path than K9's
+// barrier) and nothing to reset (comparisons are on the signed difference, so the 32-bit counter may wrap).
+// Bounded spin: a lost arrival traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier_cl(unsigned int* ticket, unsigned int n_ctas) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int old = atomicAdd(bar, 1u);
-        if (old == n_ctas - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        const unsigned int target = (t / n_ctas + 1u) * n_ctas;
+        if (t + 1u != target) {
             const long long t0 = clock64();
-            while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == my_gen)
+            while ((int)(*reinterpret_cast<volatile unsigned int*>(ticket) - target) < 0)
                 if (clock64() - t0 > 4000000000LL) __trap();
         }
         __threadfence();
@@ -233,8 +234,6 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
     const int rank = CL > 1 ? (int)cluster_rank() : 0;
     const int tile = blockIdx.x / CL, chain = blockIdx.y;
     const int row0 = tile * RT;
-    unsigned int my_gen = 0;
-    if (a.fuse_update && tid == 0) my_gen = *reinterpret_cast<volatile unsigned int*>(a.bar + 1);
 
     float* x_s   = sm;                                   // [RT][d_in]
     float* f_s   = x_s + (K10_XS(a) ? ((RT * a.d_in + 3) & ~3) : 0);       // [RT][kFS]   F_l / dF_l / raw T_l (fp32)
@@ -266,6 +265,35 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
 #define K10_STAMP() do { if (a.timing && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.timing[tsi] = clock64(); ++tsi; } while (0)
     K10_STAMP();
 
+    // ---- set-up.  The global loads this CTA waits for first (its input rows, the length-scales) are issued BEFORE the L2
+    //      warm-up loops and parked in registers, so their round trip runs under the prefetch instructions
+    constexpr int kXR = 8;
+    const int nx = RT * a.d_in;
+    const bool x_regs = K10_XS(a) && nx <= kXR * kT;
+    float xr[kXR];
+    if (x_regs) {
+#pragma unroll
+        for (int u = 0; u < kXR; ++u) {
+            const int e = tid + u * kT;
+            xr[u] = 0.f;
+            if (e < nx) {                                             // rows of the tile are contiguous in X: element e of the tile
+                const int r = e / a.d_in;
+                if (row0 + r < a.B) xr[u] = __ldg(X + (int64_t)row0 * a.d_in + e);
+            }
+        }
+    }
+    const bool hyp_regs = L * a.dmax <= kT;              // one (layer, input column) per thread: length-scale and mean
+    bool hyp_ok = false;
+    float ls_r = 0.f, mean_r = 0.f;
+    if (hyp_regs && tid < L * a.dmax) {
+        const int l = tid / a.dmax, q = tid - l * a.dmax;
+        const ClLayer& y = a.layer[l];
+        hyp_ok = q < y.d_prev + y.d_x;
+        if (hyp_ok) {
+            ls_r = __ldg(y.log_inv_ls + chain * a.h_cs + q);
+            if (K10_MEAN(y)) mean_r = __ldg(y.mean + chain * a.h_cs + q);
+        }
+    }
     // ---- L2 warm-up: this CTA's slices of z and W of every layer (first touch after an L2 flush is an HBM round trip)
     for (int l = 0; l < L; ++l) {
         const ClLayer& y = a.layer[l];
@@ -291,7 +319,11 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         const int nline = (RT * ycols + 31) >> 5;
         if (tid < nline && row0 < a.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(Y + (int64_t)row0 * ycols + 32 * tid));
     }
-    if (K10_XS(a))
+    if (x_regs) {
+#pragma unroll
+        for (int u = 0; u < kXR; ++u)
+            if (tid + u * kT < nx) x_s[tid + u * kT] = xr[u];
+    } else if (K10_XS(a))
         for (int e = tid; e < RT * a.d_in; e += kT) {
             const int r = e / a.d_in, q = e - r * a.d_in;
             x_s[e] = (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
@@ -301,13 +333,16 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
         if (K10_XS(a)) return x_s[r * a.d_in + q];
         return (row0 + r) < a.B ? __ldg(X + (int64_t)(row0 + r) * a.d_in + q) : 0.f;
     };
-    for (int e = tid; e < L * a.dmax; e += kT) {
-        const int l = e / a.dmax, q = e - l * a.dmax;
-        const ClLayer& y = a.layer[l];
-        const bool ok = q < y.d_prev + y.d_x;
-        s_all[e] = ok ? expf(__ldg(y.log_inv_ls + chain * a.h_cs + q)) : 0.f;
-        m_all[e] = (ok && K10_MEAN(y)) ? __ldg(y.mean + chain * a.h_cs + q) : 0.f;
-    }
+    if (hyp_regs) {
+        if (tid < L * a.dmax) { s_all[tid] = hyp_ok ? expf(ls_r) : 0.f; m_all[tid] = mean_r; }
+    } else
+        for (int e = tid; e < L * a.dmax; e += kT) {
+            const int l = e / a.dmax, q = e - l * a.dmax;
+            const ClLayer& y = a.layer[l];
+            const bool ok = q < y.d_prev + y.d_x;
+            s_all[e] = ok ? expf(__ldg(y.log_inv_ls + chain * a.h_cs + q)) : 0.f;
+            m_all[e] = (ok && K10_MEAN(y)) ? __ldg(y.mean + chain * a.h_cs + q) : 0.f;
+        }
     __syncthreads();
 
     // A operand of a layer: (in * s) split hi / lo, K zero-padded to a multiple of 8; in = [F_{l-1}, X].  The X part (and
@@ -781,8 +816,16 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
             mo0 = *reinterpret_cast<const float4*>(a.upd.mom + chain * a.upd.cs + (vf << 2));
             sgmcmc_draw_vec(a.upd, chain, vf, e0, mo0);
         }
-        grid_barrier_cl(a.bar, my_gen, gridDim.x * gridDim.y);
+        grid_barrier_cl(a.bar + 2, gridDim.x * gridDim.y);      // word 2 of the barrier block (K9 owns words 0 and 1)
         K10_STAMP();
+        if (a.u_out != nullptr && blockIdx.x == 0 && tid >= kT - 32) {  // minibatch log-likelihood, fixed order: on the last warp,
+            const int n_tiles = gridDim.x / CL;                         // which has no vector of the update to do in most shapes
+            const int ln = tid - (kT - 32);
+            float sll = 0.f;
+            for (int i = ln; i < n_tiles; i += 32) sll += __ldcg(a.ll_part + chain * a.ll_cs + i);
+            sll = warp_sum(sll);
+            if (ln == 0) a.u_out[chain] = sll;
+        }
         if (lpv8) {
             for (int64_t vb = v0; vb < v1; vb += kT / 8) {
                 const int64_t v = vb + (tid >> 3);
@@ -807,13 +850,6 @@ __global__ void __launch_bounds__(kT, 1) k10_step_cluster(const __grid_constant_
                 const float4 gr = slab_sum_lane<1>(grad, a.upd.part_stride, a.upd.n_part, 0, v << 2);
                 sgmcmc_apply_vec(a.upd, tab, chain, v, gr, th, mo, e);
             }
-        }
-        if (a.u_out != nullptr && blockIdx.x == 0 && tid < 32) {        // minibatch log-likelihood, fixed order
-            const int n_tiles = gridDim.x / CL;
-            float s = 0.f;
-            for (int i = tid; i < n_tiles; i += 32) s += __ldcg(a.ll_part + chain * a.ll_cs + i);
-            s = warp_sum(s);
-            if (tid == 0) a.u_out[chain] = s;
         }
         K10_STAMP();
     }
