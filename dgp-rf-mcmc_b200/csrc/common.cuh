@@ -36,6 +36,9 @@ struct ProfScope {
 
 // Opt-in dynamic shared-memory limit of a kernel, remembered per (kernel, device) and only ever raised (api.cu).
 int dgprf_ensure_smem(const void* kernel, size_t smem);
+// Signature of the process environment (api.cu): key of the per-thread plan caches, so that a debug switch set or cleared
+// between two calls is seen by the next call.
+uint64_t dgprf_env_signature(void);
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }

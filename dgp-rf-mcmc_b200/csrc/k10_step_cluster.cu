@@ -135,36 +135,51 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
                               float* gwpart, int64_t gw_cs, int64_t gw_ss, float* ll_part, int64_t ll_cs,
                               const UpdArgs* upd, const dgprf_segment* segs, int n_seg, unsigned int* bar, float* u_out,
                               bool* fused, cudaStream_t st) {
-    ClPlan p;
-    DGPRF_REQUIRE(make_plan(m, B, &p), "step_cluster: model not eligible");
-    ClArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n_layers = m->n_layers; a.likelihood = m->likelihood; a.B = B; a.d_in = m->d_in; a.d_out = m->d_out; a.CL = p.CL;
-    a.h_cs = m->h_cs; a.w_cs = m->w_cs;
-    a.X = X; a.x_cs = x_cs; a.Y = Y; a.y_cs = y_cs;
-    a.lik_log_var = m->likelihood == DGPRF_LIK_GAUSSIAN ? m->h_base + m->off_lik_log_var : nullptr;
-    a.gwpart = gwpart; a.gw_cs = gw_cs; a.gw_ss = gw_ss; a.ll_part = ll_part; a.ll_cs = ll_cs;
-    a.inv_B = 1.f / (float)B;
-    int lda = 0, dmax = 0, ncs = 0;
-    const size_t smem = plan_smem(m, p.MT, p.CL, &lda, &dmax, &ncs);
-    a.lda = lda; a.dmax = dmax; a.ncs = ncs; a.x_in_smem = x_staged(m, p.MT) ? 1 : 0;
-    const int NJM = ncs <= 8 ? 1 : (ncs <= 16 ? 2 : 4);          // ncs = 8 x the most tiles any exchanged matrix of the model has
-    int n_rbf = 0;
-    for (int l = 0; l < m->n_layers; ++l) n_rbf += m->layer[l].kind == DGPRF_KIND_RBF ? 1 : 0;
-    const int KIND = n_rbf == m->n_layers ? 0 : 2;
-    int64_t phis = 0;
-    for (int l = 0; l < m->n_layers; ++l) {
-        const dgprf_layer& y = m->layer[l];
-        ClLayer& s = a.layer[l];
-        s.kind = y.kind; s.d_prev = y.d_prev; s.d_x = y.d_x; s.M = y.M; s.g = y.g; s.has_mean = y.has_mean;
-        s.cols = layer_cols(y.M, p.CL); s.ldp = layer_ldp(y.kind, s.cols);
-        s.phi_off = (int32_t)phis;
-        phis += (int64_t)16 * p.MT * s.ldp;
-        s.z = y.z; s.z_cs = y.z_cs;
-        s.log_inv_ls = m->h_base + y.off_log_inv_ls; s.log_amp = m->h_base + y.off_log_amp;
-        s.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
-        s.W = m->w_base + y.off_W; s.off_W = y.off_W;
+    // Everything that depends on (model description, B, environment) only -- geometry, shared-memory layout, the per-layer
+    // argument block, the debug switches -- is built once per thread and re-used until one of the three changes: a sampler
+    // calls this tens of thousands of times per second with nothing but the minibatch pointers and the step scalars changing.
+    struct Cached { bool ok; dgprf_model m; int B; uint64_t env; ClPlan p; ClArgs a; size_t smem; int NJM, KIND; bool no_fused, timing; };
+    static thread_local Cached c = {};
+    const uint64_t env = dgprf_env_signature();
+    if (!(c.ok && c.B == B && c.env == env && memcmp(&c.m, m, sizeof(*m)) == 0)) {
+        c.ok = false;
+        DGPRF_REQUIRE(make_plan(m, B, &c.p), "step_cluster: model not eligible");
+        ClArgs& a = c.a;
+        memset(&a, 0, sizeof(a));
+        a.n_layers = m->n_layers; a.likelihood = m->likelihood; a.B = B; a.d_in = m->d_in; a.d_out = m->d_out; a.CL = c.p.CL;
+        a.h_cs = m->h_cs; a.w_cs = m->w_cs;
+        a.lik_log_var = m->likelihood == DGPRF_LIK_GAUSSIAN ? m->h_base + m->off_lik_log_var : nullptr;
+        a.inv_B = 1.f / (float)B;
+        int lda = 0, dmax = 0, ncs = 0;
+        c.smem = plan_smem(m, c.p.MT, c.p.CL, &lda, &dmax, &ncs);
+        a.lda = lda; a.dmax = dmax; a.ncs = ncs; a.x_in_smem = x_staged(m, c.p.MT) ? 1 : 0;
+        c.NJM = ncs <= 8 ? 1 : (ncs <= 16 ? 2 : 4);          // ncs = 8 x the most tiles any exchanged matrix of the model has
+        int n_rbf = 0;
+        for (int l = 0; l < m->n_layers; ++l) n_rbf += m->layer[l].kind == DGPRF_KIND_RBF ? 1 : 0;
+        c.KIND = n_rbf == m->n_layers ? 0 : 2;
+        int64_t phis = 0;
+        for (int l = 0; l < m->n_layers; ++l) {
+            const dgprf_layer& y = m->layer[l];
+            ClLayer& s = a.layer[l];
+            s.kind = y.kind; s.d_prev = y.d_prev; s.d_x = y.d_x; s.M = y.M; s.g = y.g; s.has_mean = y.has_mean;
+            s.cols = layer_cols(y.M, c.p.CL); s.ldp = layer_ldp(y.kind, s.cols);
+            s.phi_off = (int32_t)phis;
+            phis += (int64_t)16 * c.p.MT * s.ldp;
+            s.z = y.z; s.z_cs = y.z_cs;
+            s.log_inv_ls = m->h_base + y.off_log_inv_ls; s.log_amp = m->h_base + y.off_log_amp;
+            s.mean = y.has_mean ? m->h_base + y.off_mean : nullptr;
+            s.W = m->w_base + y.off_W; s.off_W = y.off_W;
+        }
+        c.no_fused = getenv("DGPRF_NO_FUSED_UPDATE") != nullptr;
+        c.timing = getenv("DGPRF_K10_TIMING") != nullptr;
+        memcpy(&c.m, m, sizeof(*m)); c.B = B; c.env = env; c.ok = true;
     }
+    const ClPlan& p = c.p;
+    const size_t smem = c.smem;
+    const int NJM = c.NJM, KIND = c.KIND;
+    ClArgs a = c.a;
+    a.X = X; a.x_cs = x_cs; a.Y = Y; a.y_cs = y_cs;
+    a.gwpart = gwpart; a.gw_cs = gw_cs; a.gw_ss = gw_ss; a.ll_part = ll_part; a.ll_cs = ll_cs;
     dim3 grid(p.n_tiles * p.CL, m->n_chains);
     SegTable tab;
     memset(&tab, 0, sizeof(tab));
@@ -173,7 +188,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     // under its injection the clustered geometries run unfused (K10 + K5), everything else is unchanged.
     static const bool under_ncu = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
                                   getenv("NV_NSIGHT_INJECTION_PORT_BASE");
-    if (upd != nullptr && !getenv("DGPRF_NO_FUSED_UPDATE") && !(under_ncu && p.CL > 1)) {
+    if (upd != nullptr && !c.no_fused && !(under_ncu && p.CL > 1)) {
         static int cached[16][3][5][9];                  // [device][MT][NJM][CL] (the feature-map kind does not change the resources) -> co-resident CTAs + 1 (0: not yet queried) ...
         static size_t cached_smem[16][3][5][9];          // ... for this shared-memory size
         int dev = 0;
@@ -184,7 +199,7 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
             cap = coresident_any(p.MT, NJM, KIND, p.CL, smem);
             if (dev < 16) { cached[dev][p.MT][NJM][p.CL] = cap + 1; cached_smem[dev][p.MT][NJM][p.CL] = smem; }
         }
-        if (getenv("DGPRF_K10_TIMING") && dbg_calls_peek() == 0)
+        if (c.timing && dbg_calls_peek() == 0)
             fprintf(stderr, "k10: MT %d CL %d grid %u x %u smem %zu co-resident cap %d\n", p.MT, p.CL, grid.x, grid.y, smem, cap);
         if ((int64_t)grid.x * grid.y <= cap) {
             const int rc = dgprf_build_segtable(segs, n_seg, upd->n, &tab);
@@ -196,21 +211,21 @@ int dgprf_launch_step_cluster(const dgprf_model* m, const float* X, int64_t x_cs
     }
     static long long* dbg = nullptr;                     // DGPRF_K10_TIMING=1: print phase cycle counts (debug only)
     int& dbg_calls = g_dbg_calls;
-    if (getenv("DGPRF_K10_TIMING") && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+    if (c.timing && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
     a.timing = dbg;
     int rc;
     {
         ProfScope _ps("k10_step_cluster", st);
         rc = launch_any(p.MT, NJM, KIND, a, tab, grid, smem, a.fuse_update != 0, st);
         if (rc != DGPRF_OK && a.fuse_update) {           // cooperative + cluster launch refused: run unfused, K5 follows
-            if (getenv("DGPRF_K10_TIMING")) fprintf(stderr, "k10: fused launch refused: %s\n", dgprf_last_error());
+            if (c.timing) fprintf(stderr, "k10: fused launch refused: %s\n", dgprf_last_error());
             a.fuse_update = 0;
             *fused = false;
             rc = launch_any(p.MT, NJM, KIND, a, tab, grid, smem, false, st);
         }
     }
     if (rc) return rc;
-    const char* e_at = getenv("DGPRF_K10_TIMING");
+    const char* e_at = c.timing ? getenv("DGPRF_K10_TIMING") : nullptr;
     if (dbg && ++dbg_calls == (e_at && atoi(e_at) > 1 ? atoi(e_at) : 30)) {
         long long h[64];
         cudaStreamSynchronize(st);

@@ -123,7 +123,14 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter is ~10x cheaper than building a
+    torch.cuda.Stream object: this sits on the per-step path of the sampler)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

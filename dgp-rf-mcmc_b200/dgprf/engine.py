@@ -25,6 +25,12 @@ from . import _ffi
 from .variable import out
 
 
+# How pinned host minibatches reach the kernels (read once, at import: these are A/B switches, not per-call options):
+# 2 = copied on a side stream under the previous step's kernels (default), 1 = read in place over the bus
+# (DGPRF_ZERO_COPY_READ), 0 = in-order staging copies (DGPRF_NO_ZERO_COPY).
+_ZC_MODE = 0 if os.environ.get("DGPRF_NO_ZERO_COPY") else (1 if os.environ.get("DGPRF_ZERO_COPY_READ") else 2)
+
+
 def _r4(n: int) -> int:
     return (n + 3) // 4 * 4
 
@@ -121,6 +127,7 @@ class Engine:
         self._staging: Dict = {}
         self._inflight = collections.deque()     # host minibatches the GPU may still be reading: (event | None, tensors)
         self._held = 0
+        self._u_pinned = None
         self._model = None
         self._scratch = torch.zeros(max(4, self.C), **f32)
         # segment tables: name -> (offset, length, mass, flags)
@@ -399,18 +406,22 @@ class Engine:
         fn, head, mid, tail = st[0], st[1], st[2], st[3]
         # pinned host tensors: copied on a side stream under the previous step's kernels (mode 2; DGPRF_ZERO_COPY_READ=1:
         # read in place by the kernels, mode 1); pageable ones go through in-order staging copies (mode 0)
-        zc = 2 if (X_host.is_pinned() and Y_host.is_pinned() and (u_host is None or u_host.is_pinned())) else 0
-        if zc and os.environ.get("DGPRF_NO_ZERO_COPY"):
-            zc = 0
-        elif zc and os.environ.get("DGPRF_ZERO_COPY_READ"):
-            zc = 1
+        zc = _ZC_MODE if (X_host.is_pinned() and Y_host.is_pinned() and (u_host is None or self._pinned_out(u_host))) else 0
         rc = fn(*head, X_host.data_ptr(), Y_host.data_ptr(), *mid[0], zc, *mid[1], lr, data_size, momentum_decay, temperature,
                 1 if resample else 0, seed, step, *tail, u_host.data_ptr() if u_host is not None else None,
-                torch.cuda.current_stream().cuda_stream)
+                _ffi.stream_ptr())
         if rc:
             _ffi.check(rc)
         if zc:
             self._hold(X_host, Y_host, u_host)
+
+    def _pinned_out(self, u_host) -> bool:
+        """is_pinned() of the output word, remembered for the tensor last seen (a sampler passes the same one every step)."""
+        c = self._u_pinned
+        if c is not None and c[0] is u_host:
+            return c[1]
+        self._u_pinned = (u_host, u_host.is_pinned())
+        return self._u_pinned[1]
 
     def _hold(self, *tensors):
         """Keep zero-copy host buffers alive until the GPU is done with them: every 8th step records an event; entries
