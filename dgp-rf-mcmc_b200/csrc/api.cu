@@ -108,6 +108,7 @@ struct LayerWs {
     int tc_cols;   // 0: SIMT forward; 32 | 64: tensor-core forward with that column-tile width
     int64_t n_phi, n_fpart, n_dpart, n_tpart, n_rpart;       // floats per chain
     size_t phi, fpart, dpart, tpart, rpart;                  // byte offsets of the [C][...] regions
+    int phi_blocked;                                         // saved features in the tile-blocked layout (both sides pipelined)
     int tc2;                                                 // pipelined TC forward: prepped operand buffers below
     int64_t n_zt, n_wt, n_at, n_ot; size_t zt, wt, at, ot;
     int64_t n_wp; size_t wp; int bwd2;                       // pipelined TC backward: padded W rows
@@ -179,6 +180,11 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
         }
         if (mode >= DGPRF_MODE_TRAIN) {
             s.n_phi = (int64_t)B * layer_F(y);
+            // both sides of the saved-feature round trip are the pipelined kernels: keep it tile-blocked (kernels.cuh)
+            if (s.tc2 && s.bwd2 && !getenv("DGPRF_PHI_ROWMAJOR") && !getenv("DGPRF_TC2_DIRECT_STORE")) {
+                s.phi_blocked = 1;
+                s.n_phi = dgprf_phi_blocked_floats(B, y.M, y.kind);
+            }
             s.phi = take(s.n_phi);
             if (l > 0) { s.n_dpart = (int64_t)s.CS * B * y.d_prev; s.dpart = take(s.n_dpart); }
         }
@@ -350,6 +356,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         a.W = m->w_base + y.off_W; a.w_cs = m->w_cs;
         a.Phi = mode >= DGPRF_MODE_TRAIN ? wsf(ws, w.L[l].phi) : nullptr;
         a.phi_cs = w.L[l].n_phi;
+        a.phi_blocked = (mode >= DGPRF_MODE_TRAIN) ? w.L[l].phi_blocked : 0;
         a.Fpart = wsf(ws, w.L[l].fpart); a.fpart_cs = w.L[l].n_fpart;
         if (w.L[l].tc2) {
             a.prepped = prepped ? 1 : 0;
@@ -360,14 +367,19 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         int rc;
         if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) {                                                // pipelined
             if (l > 0 && a.Fprev.n_slabs > 1 && w.n_fsum > 0 && a.d <= 128) {      // (the WIDE variant's input split sums the slabs itself)
-                // every CTA of a row block reads the whole input tile: sum the partial slabs of F_{l-1} once
+                // every CTA of a row block reads the whole input tile: sum the partial slabs of F_{l-1} once (even two slabs:
+                // adding them in the CTA's own prologue costs a second dependent load round per CTA -- measured +50 us per
+                // layer at 65 536 rows against an 11 us launch)
                 rc = dgprf_launch_sum_slabs(a.Fprev, B, y.d_prev, wsf(ws, w.fsum), w.n_fsum, m->n_chains, st);
                 if (rc) return rc;
                 a.Fprev.ptr = wsf(ws, w.fsum); a.Fprev.cs = w.n_fsum; a.Fprev.ss = 0; a.Fprev.n_slabs = 1;
             }
             rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);
         }
-        else rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
+        else {
+            DGPRF_REQUIRE(!a.phi_blocked, "layer %d: blocked saved features without the pipelined forward", l);
+            rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
+        }
         if (rc) return rc;
     }
     if (F_out) {
@@ -442,7 +454,7 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
             a.dF.ptr = wsf(ws, w.L[l + 1].dpart); a.dF.cs = w.L[l + 1].n_dpart;
             a.dF.ss = (int64_t)B * y.g; a.dF.ld = y.g; a.dF.n_slabs = w.L[l + 1].CS;
         }
-        a.Phi = wsf(ws, w.L[l].phi); a.phi_cs = w.L[l].n_phi;
+        a.Phi = wsf(ws, w.L[l].phi); a.phi_cs = w.L[l].n_phi; a.phi_blocked = w.L[l].phi_blocked;
         a.z = y.z; a.z_cs = y.z_cs;
         a.log_inv_ls = m->h_base + y.off_log_inv_ls;
         a.log_amp = m->h_base + y.off_log_amp;
@@ -465,7 +477,10 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
             }
             rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
         }
-        else rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
+        else {
+            DGPRF_REQUIRE(!a.phi_blocked, "layer %d: blocked saved features without the pipelined backward", l);
+            rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
+        }
         if (rc) return rc;
         if (hyper) {
             HypArgs h;

@@ -96,6 +96,7 @@ struct FwdArgs {
     const float* log_inv_ls; const float* log_amp; const float* mean; int64_t h_cs;
     const float* W;  int64_t w_cs;       // [F, g]
     float* Phi;      int64_t phi_cs;     // [B, F] nullable
+    int32_t phi_blocked;                 // saved features in the tile-blocked layout (dgprf_phi_blocked_floats) instead of [B, F]
     float* Fpart;    int64_t fpart_cs;   // [CS][B][g]
     float* zt; int64_t zt_cs; float* wt; // pipelined TC forward: prepped z^T hi/lo [2][M][128] and W^T [NG][F] (workspace)
     float* at; float* ot;                // ... WIDE variant: input hi/lo [2][B][Kp] and Omega^T hi/lo [2][M][Kp]
@@ -106,6 +107,7 @@ struct BwdArgs {
     int32_t kind, B, d_prev, d_x, d, M, g, F, CS, RS, ldx, has_mean, hyper;
     SlabMat dF;                          // dU/dF_l  (ld = g)
     const float* Phi; int64_t phi_cs;    // saved features [B, F]
+    int32_t phi_blocked;                 // ... or in the tile-blocked layout the pipelined forward wrote
     const float* z;   int64_t z_cs;
     const float* log_inv_ls; const float* log_amp; const float* mean; int64_t h_cs;
     const float* W;   int64_t w_cs;

@@ -37,6 +37,11 @@ constexpr uint32_t V2_TMEM_COLS = 512;            // A_hi 128 | A_lo 128 | D1 2x
 constexpr int V2_RING = 2 * V2_BLK + 2 * V2_BBLK; // WIDE k-block slot: A hi 16K | A lo 16K | Omega hi 8K | Omega lo 8K
 
 namespace tc {
+// 32-byte store (sm_100+): one full sector per lane
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -98,7 +103,14 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     // of tile t reads its tile while the epilogue writes tile t+1 into the other one.  With one tile the period of a tile is
     // "store reads 64 KB" + "epilogue writes 64 KB" back to back (profiles/r02_summary.md section B).
     const int NSW = NSW_ & 0xff;
-    const bool direct_store = (NSW_ & 0x100) != 0;
+    const bool direct_store = (NSW_ & 0x100) != 0 && !a.phi_blocked;      // (the experiment writes the row-major layout)
+    // NSW_ bit 11 (DGPRF_TC2_REG_STORE=1, an experiment kept for A/B runs; tile-blocked layout only): the epilogue warps store
+    // the saved features from registers with 256-bit stores.  In the blocked layout a thread's 16 columns are 64 contiguous
+    // bytes of a 128-byte row and a warp's 32 rows are consecutive, so a warp covers a dense 4 KB region per block and the
+    // Phi tile in shared memory is free as soon as GEMM #2 retires.  Measured at configs[4] layer scale: 0.78 ms against
+    // 0.635 ms with the TMA store -- every store instruction is still 32 separate 32-byte requests and the epilogue warps,
+    // which are the critical path, stall on the LSU queue; the asynchronous TMA store stays the default.
+    const bool reg_store = (NSW_ & 0x800) != 0 && a.phi_blocked && a.Phi != nullptr;
     const int NPHI = (NSW_ & 0x200) ? 2 : 1;
     // NSW_ bit 10 (non-WIDE): the z operand streams through a ring of NS1 k-block slots [hi 8 KB | lo 8 KB] instead of whole
     // 64 KB tiles, which is what frees the shared memory for the second Phi tile
@@ -126,6 +138,9 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     const int chain = blockIdx.z, cs = blockIdx.y, row0 = blockIdx.x * V2_BM;
     // debug timeline (DGPRF_TC2_TIMELINE=1): clock stamps of CTA 0, first 16 tiles, 12 events per tile
 #define TL(t, ev) do { if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) tl[(t) * 12 + (ev)] = clock64(); } while (0)
+    // whole-CTA phase stamps (thread 0): start | barriers + TMEM ready | input tile in smem | A operand in TMEM | last tile's epilogue | end
+#define TLC(ev) do { if (tl != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tl[16 * 12 + (ev)] = clock64(); } while (0)
+    TLC(0);
     const float* X = a.X + chain * a.x_cs;
     const float* ls = a.log_inv_ls + chain * a.h_cs;
     const float* mean = a.has_mean ? a.mean + chain * a.h_cs : nullptr;
@@ -163,6 +178,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    TLC(1);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm_ahi = tmem_base, tm_alo = tmem_base + 128, tm_d1 = tmem_base + (WIDE ? 0 : 256), tm_d2 = tmem_base + (WIDE ? 128 : 384);
 
@@ -205,6 +221,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             }
         }
         __syncthreads();
+        TLC(2);
         if (warp < V2_EPI_WARPS) {
             const int lq = warp & 3, kq = warp >> 2;              // TMEM lane quarter, 32-column K quarter
             const int r = 32 * lq + lane;
@@ -237,6 +254,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    TLC(3);
 
     constexpr uint32_t IDESC1 = tc::make_idesc_tf32(V2_BM, V2_BN);
     constexpr uint32_t IDESC2 = tc::make_idesc_tf32(V2_BM, NG);
@@ -296,6 +314,17 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                         }
                 }
             }
+            if (reg_store) {
+                const int nb = rbf ? 4 : 2;
+                const int64_t blk0 = ((int64_t)blockIdx.x * n_ct + (ct0 + t)) * nb;
+                float* dst = a.Phi + chain * a.phi_cs + ((blk0 + pb) * V2_BM + r) * 32 + (cq & 1) * 16;
+                tc::st_global_v8(dst, p);
+                tc::st_global_v8(dst + 8, p + 8);
+                if (rbf) {
+                    tc::st_global_v8(dst + 2 * V2_BM * 32, f1);
+                    tc::st_global_v8(dst + 2 * V2_BM * 32 + 8, f1 + 8);
+                }
+            }
             const int pbuf = t % NPHI;
             uint8_t* sPhiT = sPhi + pbuf * 4 * V2_BLK;
             tc::mbar_wait(phi_empty + pbuf, ((t / NPHI) & 1) ^ 1);   // GEMM #2 and the store of the tile last held here are done
@@ -313,6 +342,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             if (lane == 0) tc::mbar_arrive(phi_full + pbuf);
             if (tid == 0) TL(t, 4);
         }
+        TLC(4);
         // ---- final: F partial slab of this column split ----
         if (a.do_gemm2 && n_my > 0 && warp < 4) {
             tc::mbar_wait(d2_full, 0);
@@ -498,13 +528,23 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     } else {
         // ===================================== STORE WARP =====================================
         if (tc::elect_one()) {
-            const bool storing = a.Phi != nullptr && !direct_store;
+            const bool storing = a.Phi != nullptr && !direct_store && !reg_store;
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (ct0 + t) * V2_BN;
                 const int pbuf = t % NPHI;
                 tc::mbar_wait(phi_full + pbuf, (t / NPHI) & 1);
                 if (storing) {
                     const uint8_t* sPhiT = sPhi + pbuf * 4 * V2_BLK;
+                    if (a.phi_blocked) {
+                        // tile-blocked layout: block (row block, column tile, blk) starts at row ((rb * n_ct + ct) * nb + blk) * 128 of a
+                        // [rows, 32] matrix; dead columns of a ragged last tile are stored as the zeros the epilogue wrote
+                        const int nb = rbf ? 4 : 2;
+                        const int blk0 = ((int)blockIdx.x * n_ct + (ct0 + t)) * nb;
+                        for (int b = 0; b < 2; ++b) {
+                            tc::tma_store_3d(&map_cos, tc::smem_u32(sPhiT + b * V2_BLK), 0, (blk0 + b) * V2_BM, chain);
+                            if (rbf) tc::tma_store_3d(&map_cos, tc::smem_u32(sPhiT + (2 + b) * V2_BLK), 0, (blk0 + 2 + b) * V2_BM, chain);
+                        }
+                    } else
                     for (int b = 0; b < 2; ++b) {
                         if (c0 + 32 * b >= a.M) break;
                         tc::tma_store_3d(&map_cos, tc::smem_u32(sPhiT + b * V2_BLK), c0 + 32 * b, row0, chain);
@@ -527,6 +567,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     }
     tc::tc_fence_before();
     __syncthreads();
+    TLC(5);
     if (warp == V2_EPI_WARPS) tc::tmem_dealloc(tmem_base, V2_TMEM_COLS);
 }
 
@@ -635,6 +676,25 @@ k_prep_wide_o(const FwdArgs a, int Kp, float* __restrict__ ot) {
         }
 }
 
+int64_t dgprf_phi_blocked_floats(int B, int M, int kind) {
+    return (int64_t)ceil_div(B, V2_BM) * ceil_div(M, V2_BN) * (kind == DGPRF_KIND_RBF ? 4 : 2) * (V2_BM * 32);
+}
+
+// tensor maps of the saved-feature store: row-major [B, F] (cos half | sin half) or the tile-blocked layout (one map)
+static int make_phi_maps(const FwdArgs& a, int n_chains, CUtensorMap* mc, CUtensorMap* ms) {
+    if (a.phi_blocked) {
+        const int64_t n = dgprf_phi_blocked_floats(a.B, a.M, a.kind);
+        DGPRF_REQUIRE(a.phi_cs >= n, "blocked saved-feature buffer too small: %lld < %lld floats", (long long)a.phi_cs, (long long)n);
+        const int rc = dgprf_make_tmap_3d(mc, a.Phi, 32, (uint64_t)(n / 32), n_chains, 32, a.phi_cs, V2_BM);
+        *ms = *mc;
+        return rc;
+    }
+    int rc = dgprf_make_tmap_3d(mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+    if (rc) return rc;
+    if (a.kind == DGPRF_KIND_RBF) rc = dgprf_make_tmap_3d(ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+    return rc;
+}
+
 static size_t tc2_smem_bytes(int NG, int n_kb, int ns1) {
     return 1024 + V2_HDR + 4 * (size_t)V2_BLK + 2 * 4 * (size_t)NG * 128 + (size_t)ns1 * 2 * n_kb * V2_BBLK;
 }
@@ -667,12 +727,8 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     memset(&mc, 0, sizeof(mc));
     memset(&ms, 0, sizeof(ms));
     if (a.Phi != nullptr) {
-        int rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+        const int rc = make_phi_maps(a, n_chains, &mc, &ms);
         if (rc) return rc;
-        if (a.kind == DGPRF_KIND_RBF) {
-            rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
-            if (rc) return rc;
-        }
     }
     int rc = dgprf_make_tmap_3d(&mo, a.ot, Kp, a.M, 2 * n_chains, Kp, (uint64_t)a.M * Kp, V2_BN);
     if (rc) return rc;
@@ -682,7 +738,7 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     if (rc) return rc;
     static long long* tl = nullptr;
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0), tl, mc, ms, mo, mw, ma); }
+    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0), tl, mc, ms, mo, mw, ma); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -700,7 +756,10 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     // tile t+1 -- 0.62 -> 0.57 ms at B = 65536, d = 90, M = 4096); with four k-blocks per tile it loses to the two whole-tile
     // stages (0.65 -> 0.69 ms: shared memory has no room for a fifth slot).  DGPRF_TC2_KRING=<slots | 0> overrides.
     const char* e_kr = getenv("DGPRF_TC2_KRING");
-    int kring = a.Phi == nullptr ? 0 : (e_kr ? atoi(e_kr) : (n_kb <= 3 ? 4 : 0));
+    // (with the register-store experiment no TMA store sits on the tile's critical path: one Phi tile and two whole-tile z
+    //  stages, as in the eval-mode forward)
+    const bool regst = a.phi_blocked && getenv("DGPRF_TC2_REG_STORE");
+    int kring = a.Phi == nullptr ? 0 : (e_kr ? atoi(e_kr) : ((n_kb <= 3 && !regst) ? 4 : 0));
     if (kring > 6) kring = 6;
     const int nsw_k = getenv("DGPRF_TC2_NSW") ? atoi(getenv("DGPRF_TC2_NSW")) : 2;      // W^T ring stages next to the k-block ring (1 | 2)
     const size_t smem_kring = 1024 + V2_HDR + 8 * (size_t)V2_BLK + (size_t)(nsw_k == 1 ? 1 : 2) * 4 * (size_t)NG * 128 + (size_t)kring * 2 * V2_BBLK;
@@ -721,12 +780,8 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     memset(&mc, 0, sizeof(mc));
     memset(&ms, 0, sizeof(ms));
     if (a.Phi != nullptr) {
-        int rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
+        const int rc = make_phi_maps(a, n_chains, &mc, &ms);
         if (rc) return rc;
-        if (a.kind == DGPRF_KIND_RBF) {
-            rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, V2_BM);
-            if (rc) return rc;
-        }
     }
     int rc = dgprf_make_tmap_3d(&mz, a.zt, 128, a.M, 2 * (a.z_cs != 0 ? n_chains : 1), 128, (uint64_t)a.M * 128, V2_BN);
     if (rc) return rc;
@@ -737,15 +792,18 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
     static long long* tl = nullptr;                       // debug timeline (DGPRF_TC2_TIMELINE=1)
     static int tl_calls = 0;
-    if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, 16 * 12 * sizeof(long long)); }
-    if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0), tl, mc, ms, mz, mw, mw); }
+    if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, (16 * 12 + 8) * sizeof(long long)); }
+    if (tl) cudaMemsetAsync(tl, 0, (16 * 12 + 8) * sizeof(long long), st);
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
-        long long h[16 * 12];
+        long long h[16 * 12 + 8];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, tl, sizeof(h), cudaMemcpyDeviceToHost);
         const long long t0 = h[9];                         // producer's first stamp
+        const long long* c = h + 16 * 12;
+        fprintf(stderr, "tc2 CTA phases (cycles): barriers + TMEM alloc %lld | input tile -> smem %lld | A operand -> TMEM %lld | %d tiles %lld | F slab + drain %lld | total %lld (grid %u x %u)\n",
+                c[1] - c[0], c[2] - c[1], c[3] - c[2], (int)ceil_div(ceil_div(a.M, V2_BN), a.CS), c[4] - c[3], c[5] - c[4], c[5] - c[0], grid.x, grid.y);
         fprintf(stderr, "tc2 timeline (cycles since the producer started; train=%d)\n tile | epi: P-ready P-loaded sincos-done phi-free stored | mma: g1-go g1-issued g2-go g2-issued | prod: z-slot w-slot | g1-mmas-issued(before commits)\n", a.Phi != nullptr);
         for (int t = 0; t < 16; ++t) {
             fprintf(stderr, " %3d |", t);
@@ -785,7 +843,26 @@ int dgprf_fwd_tc2_col_splits(int tile_cols, int B, int d, int M, int g, int n_ch
     }
     const int min_tiles = getenv("DGPRF_TC2_MIN_TILES") ? atoi(getenv("DGPRF_TC2_MIN_TILES")) : (tile_cols != 64 ? 1 : 4);
     while (cs > 1 && n_ct / cs < min_tiles) --cs;
-    return n_ct / cs >= min_tiles ? cs : 0;
+    if (n_ct / cs < min_tiles) return 0;
+    if (tile_cols == 64) {
+        // Every CTA pays a fixed ~5 tile times before and after its tiles (measured at configs[4] layer scale, per-CTA stamps
+        // of DGPRF_TC2_TIMELINE: input tile -> shared memory 8.1 k cycles, A operand -> tensor memory 2.9 k, barriers + TMEM
+        // allocation 1.3 k, F slab + store drain 6.1 k; a tile is 4.35 k) and CTAs run one per SM in waves, so "as many CTAs
+        // as possible" loses when the row blocks are few: 8 192 rows ran 64 x 8 CTAs of 8 tiles in four waves (127-137 us)
+        // where 64 x 2 CTAs of 32 tiles take one.  Pick the split with the smallest  waves x (5 + tiles per CTA).
+        if (const char* e = getenv("DGPRF_TC2_CS")) {
+            const int f = atoi(e);
+            if (f >= 1 && f <= kMaxCS && f <= n_ct) return f;
+        }
+        int best = cs;
+        int64_t best_cost = -1;
+        for (int c = 1; c <= cs; ++c) {
+            const int64_t cost = ceil_div(rb * c, (int64_t)148) * (5 + ceil_div(n_ct, c));
+            if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
+        }
+        cs = best;
+    }
+    return cs;
 }
 bool dgprf_fwd_tc2_supported(const FwdArgs& a) {
     return a.wt != nullptr && (a.d <= 128 ? a.zt != nullptr : (a.at != nullptr && a.ot != nullptr)) &&

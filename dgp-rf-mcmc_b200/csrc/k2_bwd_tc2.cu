@@ -213,6 +213,14 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             auto load_phi = [&](int k) {
                 const int s = k & 1, c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
                 tc::mbar_expect_tx(phi_full + s, phi_bytes);
+                if (a.phi_blocked) {                                // tile-blocked layout (k1_fwd_tc2.cu): four contiguous 16 KB blocks
+                    const int nb = rbf ? 4 : 2;
+                    const int blk0 = ((rs + (k / n_loc) * a.RS) * n_ct + (cs + (k % n_loc) * a.CS)) * nb;
+                    for (int b = 0; b < 2; ++b) {
+                        tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, 0, (blk0 + b) * B2_BM, chain);
+                        if (rbf) tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, 0, (blk0 + 2 + b) * B2_BM, chain);
+                    }
+                } else
                 for (int b = 0; b < 2; ++b) {
                     tc::tma_load_3d(&map_cos, tc::smem_u32(sPhi + (s * 4 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
                     if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
@@ -365,7 +373,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                     o.w = pc.w > 0.f ? dc[3] * arc_scale : 0.f;
                 }
                 rsum += (o.x + o.y) + (o.z + o.w);
-                o.x = tc::to_tf32(o.x); o.y = tc::to_tf32(o.y); o.z = tc::to_tf32(o.z); o.w = tc::to_tf32(o.w);
+                o.x = tc::tf32_rn_bits(o.x); o.y = tc::tf32_rn_bits(o.y); o.z = tc::tf32_rn_bits(o.z); o.w = tc::tf32_rn_bits(o.w);
                 *reinterpret_cast<float4*>(sdP + hh * B2_BLK + tc::sw128_chunk(r, cc)) = o;
             }
             tc::tc_fence_before();
@@ -511,11 +519,19 @@ int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
     CUtensorMap mc, ms, mw, mz;
     memset(&ms, 0, sizeof(ms));
     memset(&mz, 0, sizeof(mz));
-    int rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
-    if (rc) return rc;
-    if (a.kind == DGPRF_KIND_RBF) {
-        rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
+    int rc;
+    if (a.phi_blocked) {
+        const int64_t n = dgprf_phi_blocked_floats(a.B, a.M, a.kind);
+        DGPRF_REQUIRE(a.phi_cs >= n, "blocked saved-feature buffer too small: %lld < %lld floats", (long long)a.phi_cs, (long long)n);
+        rc = dgprf_make_tmap_3d(&mc, a.Phi, 32, (uint64_t)(n / 32), n_chains, 32, a.phi_cs, B2_BM, true);
         if (rc) return rc;
+    } else {
+        rc = dgprf_make_tmap_3d(&mc, a.Phi, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
+        if (rc) return rc;
+        if (a.kind == DGPRF_KIND_RBF) {
+            rc = dgprf_make_tmap_3d(&ms, a.Phi + a.M, a.M, a.B, n_chains, a.F, a.phi_cs, B2_BM, true);
+            if (rc) return rc;
+        }
     }
     rc = dgprf_make_tmap_3d(&mw, a.wp, B2_NG, a.F, n_chains, B2_NG, (uint64_t)a.F * B2_NG, B2_BN);
     if (rc) return rc;

@@ -61,6 +61,12 @@ int64_t dgprf_fwd_tc2_at_floats(int B, int d);
 int64_t dgprf_fwd_tc2_ot_floats(int M, int d);
 int64_t dgprf_fwd_tc2_wt_floats(int F, int g);
 int dgprf_launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st);
+// Tile-blocked layout of the saved features between the pipelined forward and the pipelined backward of a layer:
+//   [row block of 128][column tile of 64][cos b0 | cos b1 | sin b0 | sin b1 (arc-cosine: b0 | b1)][128 rows][32 floats]
+// so that the four TMA boxes of a (128 x 64) tile are ONE contiguous 64 KB run in HBM instead of 4 x 128 pieces of 128
+// bytes a row pitch (32 KB) apart: the same store pattern with no compute measures 6.25 TB/s blocked against 5.1-5.3 TB/s
+// row-major (profiles/r02_tma_store_blocked.txt).  The buffer is internal to the workspace; nothing else reads it.
+int64_t dgprf_phi_blocked_floats(int B, int M, int kind);
 int dgprf_tc_tile_cols(int B, int M, int n_chains);
 bool dgprf_bwd_tc2_shape_ok(int M, int g, int d, int d_prev, int CS, int hyper);
 int64_t dgprf_bwd_tc2_wp_floats(int F);

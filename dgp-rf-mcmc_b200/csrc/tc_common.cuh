@@ -36,6 +36,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// Round-to-nearest tf32 for an operand the tensor core reads from shared / tensor memory: kind::tf32 ignores the low 13
+// mantissa bits, so adding half a tf32 ulp to the bit pattern is all it takes (ties away from zero, the result cvt.rna
+// gives for every finite input; cvt.rna.tf32.f32 itself is a four-instruction sequence with an Inf / NaN guard on sm_100a).
+// Used where the conversion sits in an issue-bound epilogue.
+__device__ __forceinline__ float tf32_rn_bits(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
 // ---- UMMA descriptors ------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO=1024>>4 |
 // version=1 (bits 46-47) | layout_type=2 (bits 61-63)

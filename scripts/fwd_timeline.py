@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "dgp-rf-mcmc_b200"))
 import torch
 from dgprf import _ffi
 from dgprf.engine import Engine, ModelSpec
-B, d, M, g = 65536, 120, 4096, 30
+B, d, M, g = int(os.environ.get("TL_ROWS", 65536)), int(os.environ.get("TL_D", 120)), 4096, 30
 spec = ModelSpec.build(d, g, [M], [g], ["RBF"], False, False, "gaussian")
 X = torch.randn(B, d, device="cuda")
 e = Engine(spec, 1, precision=_ffi.PREC_TF32)

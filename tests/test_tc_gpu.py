@@ -8,6 +8,8 @@ outputs, log-likelihoods and gradients agree with the oracle to max-abs error / 
 UPSTREAM layers are only bounded by 5e-2 -- the tf32 error of F (~3e-4) flips about 0.02 % of the
 downstream ReLU gates and the derivative is discontinuous there (the gradient is exact for the
 perturbed forward).  The fp32 SIMT mode keeps the 1e-4 bound for everything (tests/test_parity_gpu.py)."""
+import os
+
 import pytest
 import torch
 
@@ -96,21 +98,41 @@ def test_tc_saved_features_and_gradients(name):
     # layer-0 Phi sits right after layer-0's F partial slabs in the workspace (csrc/api.cu make_layout)
     s0 = e.spec.layers[0]
     Bn = X.shape[0]
-    ctas64 = ((Bn + 127) // 128) * min((s0.M + 63) // 64, 8)
-    CS = min((s0.M + 63) // 64, 8)                                                       # SIMT forward (col_splits) unless ...
-    n_ct, rb = (s0.M + 63) // 64, (Bn + 127) // 128                                    # dgprf_fwd_tc2_col_splits
-    if ctas64 >= 120 or rb * n_ct >= 4:
-        c2 = max(1, min((4 * 148 + rb - 1) // rb, 8, n_ct))
-        if s0.d > 128 or ctas64 < 120:
-            CS = c2
-        else:
-            while c2 > 1 and n_ct // c2 < 4:
-                c2 -= 1
-            if n_ct // c2 >= 4:
-                CS = c2
+    CS, pipelined_fwd = _fwd_col_splits(Bn, s0.M, s0.d)
     off = ((CS * Bn * s0.g * 4 + 255) // 256) * 256
-    Phi0 = ws[off:off + X.shape[0] * s0.F * 4].view(torch.float32).view(X.shape[0], s0.F)
+    n_rb, n_ct = (Bn + 127) // 128, (s0.M + 63) // 64
+    nb = 4 if s0.kind == "RBF" else 2
+    # the pipelined backward takes the layer when n_gp <= 32, d_prev <= 64 (0 for layer 0) and M % 4 == 0: both sides pipelined ->
+    # the saved features are tile-blocked [row block][column tile][cos b0 | cos b1 | sin b0 | sin b1][128][32] (csrc/kernels.cuh)
+    blocked = pipelined_fwd and s0.g <= 32 and s0.M % 4 == 0 and not os.environ.get("DGPRF_PHI_ROWMAJOR")
+    if blocked:
+        raw = ws[off:off + n_rb * n_ct * nb * 128 * 32 * 4].view(torch.float32).view(n_rb, n_ct, nb // 2, 2, 128, 32)
+        # -> [row block, row, half (cos | sin), column tile, block, column]
+        Phi0 = raw.permute(0, 4, 2, 1, 3, 5).reshape(n_rb * 128, nb // 2, n_ct * 64)[:Bn, :, :s0.M].reshape(Bn, s0.F)
+    else:
+        Phi0 = ws[off:off + Bn * s0.F * 4].view(torch.float32).view(Bn, s0.F)
     assert rel_err(Phi0, Phis[0]) < 1e-4
+
+
+def _fwd_col_splits(Bn, M, d):
+    """Column splits of the layer-0 forward (csrc/api.cu make_layout -> dgprf_fwd_tc2_col_splits) and whether it is the
+    pipelined tensor-core kernel."""
+    n_ct, rb = (M + 63) // 64, (Bn + 127) // 128
+    ctas64 = rb * min(n_ct, 8)
+    CS = min(n_ct, 8)                                                                    # SIMT forward (col_splits) unless ...
+    if M % 4 != 0 or not (ctas64 >= 120 or rb * n_ct >= 4):
+        return CS, False
+    c2 = max(1, min((4 * 148 + rb - 1) // rb, 8, n_ct))
+    if d > 128:
+        return c2, True
+    min_tiles = 4 if ctas64 >= 120 else 1
+    while c2 > 1 and n_ct // c2 < min_tiles:
+        c2 -= 1
+    if n_ct // c2 < min_tiles:
+        return CS, False
+    if ctas64 >= 120:                       # 64-wide tiles: the split with the smallest waves x (5 + tiles per CTA)
+        c2 = min(range(1, c2 + 1), key=lambda c: (-(-rb * c // 148) * (5 + -(-n_ct // c)), c))
+    return c2, True
 
 
 def test_tc_multi_chain_matches_single_chain():
