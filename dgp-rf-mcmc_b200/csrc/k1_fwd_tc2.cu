@@ -137,9 +137,10 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chain = blockIdx.z, cs = blockIdx.y, row0 = blockIdx.x * V2_BM;
     // debug timeline (DGPRF_TC2_TIMELINE=1): clock stamps of CTA 0, first 16 tiles, 12 events per tile
-#define TL(t, ev) do { if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) tl[(t) * 12 + (ev)] = clock64(); } while (0)
+    const unsigned tl_rb = (unsigned)NSW_ >> 16;         // row block whose CTA is stamped (DGPRF_TC2_TIMELINE_RB, default 0)
+#define TL(t, ev) do { if (tl != nullptr && blockIdx.x == tl_rb && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) tl[(t) * 12 + (ev)] = clock64(); } while (0)
     // whole-CTA phase stamps (thread 0): start | barriers + TMEM ready | input tile in smem | A operand in TMEM | last tile's epilogue | end
-#define TLC(ev) do { if (tl != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tl[16 * 12 + (ev)] = clock64(); } while (0)
+#define TLC(ev) do { if (tl != nullptr && tid == 0 && blockIdx.x == tl_rb && blockIdx.y == 0 && blockIdx.z == 0) tl[16 * 12 + (ev)] = clock64(); } while (0)
     TLC(0);
     const float* X = a.X + chain * a.x_cs;
     const float* ls = a.log_inv_ls + chain * a.h_cs;
@@ -192,9 +193,10 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             sSq[tid] = tid < a.d ? expf(__ldg(ls + tid)) : 0.f;
             sMean[tid] = (mean != nullptr && tid < a.d) ? __ldg(mean + tid) : 0.f;
         }
-        // 8 independent loads per thread in flight; the partial slabs of the previous layer are added slab by slab
-        // in slab order (the order of slab_load)
-        constexpr int PB = 8;
+        // The whole tile in ONE round of loads (26 per thread in flight; the partial slabs of the previous layer are added
+        // slab by slab in slab order, the order of slab_load): under the other CTAs' store streams a dependent round trip to
+        // L2 / HBM costs ~3.4 k cycles, and four rounds of 8 loads were 7 % of a CTA's lifetime at configs[4] layer scale
+        constexpr int PB = (V2_BM * 128 + V2_THREADS - 1) / V2_THREADS;
         const float* fp = a.Fprev.ptr + chain * a.Fprev.cs;
         for (int e0 = tid; e0 < V2_BM * 128; e0 += V2_THREADS * PB) {
             float v[PB];
@@ -794,7 +796,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, (16 * 12 + 8) * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, (16 * 12 + 8) * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0), tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0) | ((tl && getenv("DGPRF_TC2_TIMELINE_RB")) ? (atoi(getenv("DGPRF_TC2_TIMELINE_RB")) << 16) : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12 + 8];

@@ -116,3 +116,95 @@ def test_golden_step_vectors_reproduce():
             if k == "case":
                 continue
             assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-12), (f, k)
+
+
+# ---- the reference's own per-cycle printouts (tests/golden/make_notebook_traces.py) -----------------------------------
+def _traces():
+    return json.load(open(os.path.join(GOLDEN, "notebook_sin_demo_traces.json")))
+
+
+def sin_demo_data(seed, n_train=60, n_test=100, std_noise=0.02):
+    """The notebook's data recipe (train_regression_demo_sin.ipynb cell 1), seeded here (the notebook's draw is not)."""
+    rng = np.random.RandomState(seed)
+    X = np.concatenate([rng.uniform(-2., -1., n_train // 2), rng.uniform(1., 2., n_train - n_train // 2)])
+    Y = np.sin(np.pi * X) + rng.randn(n_train) * std_noise
+    y_mean, y_std = np.average(Y), np.std(Y)
+    Xt = np.linspace(-5., 5., n_test)
+    Yt = (np.sin(np.pi * Xt) - y_mean) / y_std
+    f = lambda a: torch.tensor(np.float32(a)).reshape(-1, 1)
+    return f(X), f((Y - y_mean) / y_std), f(Xt), f(Yt)
+
+
+def band(values, burn):
+    v = np.asarray(values[burn:], dtype=np.float64)
+    return float(np.percentile(v, 5)), float(np.median(v)), float(np.percentile(v, 95))
+
+
+def test_notebook_ll_rmse_pairs_pin_the_gaussian_likelihood():
+    """Every (mean log-likelihood, RMSE) pair the reference printed -- 1040 cycles x (train, test) -- obeys
+    LL = -0.5 log(2 pi var) - RMSE^2 / (2 var) with the notebook's variance 0.01: the oracle's Gaussian log-density
+    (likelihoods/gaussian.py:20-25, variance kept as log-variance) reproduces each printed LL from the printed RMSE."""
+    n = 0
+    for run in _traces()["runs"]:
+        llv = torch.tensor(math.log(run["config"]["lik_variance"]), dtype=torch.float64)
+        for split in ("train", "test"):
+            ll = torch.tensor(run[split + "_ll"], dtype=torch.float64)
+            rmse = torch.tensor(run[split + "_rmse"], dtype=torch.float64)
+            got = O.gaussian_log_prob(torch.zeros(len(rmse), 1, dtype=torch.float64), rmse[:, None], llv)
+            # printed in fp32 by TensorFlow: 7 significant digits of LL and of RMSE (RMSE^2 / 0.02 amplifies the latter)
+            tol = 2e-6 * (ll.abs() + 1.0) + 4e-6 * rmse ** 2 / run["config"]["lik_variance"]
+            assert bool(((got - ll).abs() <= tol).all()), float(((got - ll).abs() / tol).max())
+            n += len(ll)
+    assert n == 2080
+
+
+def _oracle_demo_chain(cfg, X, Y, n_cycles, seed):
+    """regression_train_demo (experiments/utils_training_demo.py:10-85) restated on the oracle: W only, identity
+    preconditioner, cosine cycles from step 1, momentum resampled at every cycle head; returns the train RMSE and the mean
+    train log-likelihood of the sample at the end of every cycle (what the notebook prints)."""
+    N, B = X.shape[0], 20
+    p = O.init_params(1, 1, cfg["n_hidden_layers"], cfg["n_rf"], cfg["n_gp"], None, False, "gaussian",
+                      lik_var=cfg["lik_variance"], seed=seed, dtype=torch.float64)
+    g = torch.Generator().manual_seed(1000 + seed)
+    mom = {n: torch.randn(t.shape, generator=g, dtype=torch.float64) for n, t in p.w_named()}
+    it_per_epoch = N // B
+    cycle = cfg["epochs_per_cycle"] * it_per_epoch
+    rmse, ll = [], []
+    Xd, Yd = X.double(), Y.double()
+    step_index = 0
+    for epoch in range(n_cycles * cfg["epochs_per_cycle"]):
+        perm = torch.randperm(N, generator=g)
+        for b in range(it_per_epoch):
+            idx = perm[b * B:(b + 1) * B]
+            step_index += 1
+            lr, is_end = O.cyclical_lr(cfg["lr_0"], step_index, cycle)
+            eps = {n: torch.randn(t.shape, generator=g, dtype=torch.float64) for n, t in p.w_named()}
+            res = None
+            if cfg["resample_in_cycle_head"] and step_index % cycle == 1:
+                res = {n: torch.randn(t.shape, generator=g, dtype=torch.float64) for n, t in p.w_named()}
+            _, _, p, mom = O.sgmcmc_step(p, mom, Xd[idx], Yd[idx], N, lr=float(lr), momentum_decay=cfg["momentum_decay"],
+                                         temperature=1.0, eps=eps, resample=res, analytic=True)
+            if is_end:
+                lp, se = O.eval_log_likelihood_and_se(p, Xd, Yd)
+                rmse.append(float(se.mean().sqrt())); ll.append(float(lp.mean()))
+    return rmse, ll
+
+
+def test_oracle_sampler_lands_in_the_band_of_the_reference_run():
+    """Statistical pin of the sampling path against a real run of the reference (its data set is unseeded, so this is a band,
+    not a vector): the 2-layer sin demo of train_regression_demo_sin.ipynb cell 13 printed, over 1000 cycles, a train RMSE
+    with 5 % / median / 95 % = 0.051 / 0.067 / 0.091 and a mean train log-likelihood of 0.97 / 1.16 / 1.25 (after the first
+    200 cycles).  The oracle, run through the same driver loop with the same settings on a data set from the same recipe,
+    must put its median inside that 5-95 % band.  A sampler with a wrong step size, noise scale, temperature or prior term
+    leaves it: e.g. T = 0 gives a median RMSE of ~0.03, twice the noise ~0.11."""
+    run = [r for r in _traces()["runs"] if r["cell"] == 13][0]
+    lo_r, _, hi_r = band(run["train_rmse"], 200)
+    lo_l, _, hi_l = band(run["train_ll"], 200)
+    X, Y, _, _ = sin_demo_data(seed=5)
+    rmse, ll = _oracle_demo_chain(run["config"], X, Y, n_cycles=24, seed=1)
+    _, med_r, _ = band(rmse, 8)
+    _, med_l, _ = band(ll, 8)
+    print(f"oracle median train RMSE {med_r:.4f} (reference band {lo_r:.4f} .. {hi_r:.4f}), "
+          f"median train LL {med_l:.4f} (reference band {lo_l:.4f} .. {hi_l:.4f})")
+    assert lo_r <= med_r <= hi_r
+    assert lo_l <= med_l <= hi_l
