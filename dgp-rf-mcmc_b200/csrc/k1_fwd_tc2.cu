@@ -90,6 +90,17 @@ __device__ __forceinline__ void issue_gemm2(uint32_t tm_d2, uint64_t dphi, uint6
                           (b | k4) != 0 ? 1u : acc_first);
 }
 
+// GEMM #2 of one Phi sub-tile (32 P columns: [cos block | sin block]); dw_h = descriptor of W^T block h of the tile's stage
+template <int NBLK, int NG>
+__device__ __forceinline__ void issue_gemm2_sub(uint32_t tm_d2, uint64_t dphi, uint64_t dw_h, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+            tc::umma_tf32(tm_d2, dphi + (uint32_t)((b * V2_BLK + k4 * 32) >> 4), dw_h + (uint32_t)((2 * b * NG * 128 + k4 * 32) >> 4), idesc,
+                          (b | k4) != 0 ? 1u : acc_first);
+}
+
 template <int NG, bool WIDE>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, const __grid_constant__ CUtensorMap map_cos,
@@ -115,20 +126,25 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
     // NSW_ bit 10 (non-WIDE): the z operand streams through a ring of NS1 k-block slots [hi 8 KB | lo 8 KB] instead of whole
     // 64 KB tiles, which is what frees the shared memory for the second Phi tile
     const bool KRING = !WIDE && (NSW_ & 0x400) != 0;
+    // NSW_ bit 12 (with the k-block ring; the default when the features are stored): the Phi tile is produced, consumed and
+    // stored as two SUB-TILES of 32 P columns ([cos block | sin block], 32 KB) through a ring of THREE sub-tile buffers.  The
+    // TMA store of a sub-tile then drains while the epilogue writes the next two (a whole second tile would not fit next to
+    // a z ring deep enough to keep GEMM #1 ahead: 96 KB of Phi buffers + six k-block slots instead of 128 KB + four).
+    const bool SUB3 = KRING && (NSW_ & 0x1000) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* bias_s = reinterpret_cast<float*>(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_BM * sizeof(float));
     uint8_t* sPhi = sm + V2_HDR;                         // 4 blocks [128 x 32]: cos 0,1 | sin 2,3
-    uint8_t* sW = sPhi + NPHI * 4 * V2_BLK;              // NSW stages x 4 blocks [NG x 32]
+    uint8_t* sW = sPhi + (SUB3 ? 6 : NPHI * 4) * V2_BLK; // NSW stages x 4 blocks [NG x 32]
     uint8_t* sB1 = sW + NSW * 4 * NG * 128;              // NS1 stages x [hi blocks 0..n_kb) | lo blocks 0..n_kb)] of [64 x 32]
                                                          // WIDE: NS1 k-block slots of V2_RING bytes
     uint64_t* b1_full = bars + 22;    // [6] TMA complete_tx      -> MMA
     uint64_t* b1_empty = bars + 28;   // [6] MMA commit           -> producer
     uint64_t* d1_full = bars + 6;     // [2] MMA commit           -> epilogue
     uint64_t* d1_empty = bars + 8;    // [2] epilogue warps       -> MMA
-    uint64_t* phi_full = bars + 18;   // [2] epilogue warps           -> MMA, store
-    uint64_t* phi_empty = bars + 20;  // [2] MMA commit + store warp  -> epilogue      (count 2)
+    uint64_t* phi_full = SUB3 ? bars + 0 : bars + 18;    // [2 | 3] epilogue warps           -> MMA, store
+    uint64_t* phi_empty = SUB3 ? bars + 3 : bars + 20;   // [2 | 3] MMA commit + store warp  -> epilogue      (count 2)
     uint64_t* w_full = bars + 12;     // [2] TMA complete_tx      -> MMA
     uint64_t* w_empty = bars + 14;    // [2] MMA commit           -> producer
     uint64_t* d2_full = bars + 16;    // MMA commit               -> final epilogue
@@ -169,7 +185,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             tc::mbar_init(w_full + i, 1);
             tc::mbar_init(w_empty + i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < (SUB3 ? 3 : 2); ++i) {
             tc::mbar_init(phi_full + i, V2_EPI_WARPS);
             tc::mbar_init(phi_empty + i, 2);
         }
@@ -273,6 +289,52 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
             tc::mbar_wait(d1_full + buf, (t >> 1) & 1);
             if (tid == 0) TL(t, 0);
             tc::tc_fence_after();
+            if (SUB3) {
+                // this warp's 8 columns of each 32-column half of the P tile -> registers, then D1 is free
+                float ph[2][8];
+                tc::tmem_ld8(tm_d1 + 64 * buf + ((uint32_t)(32 * lq) << 16) + 8 * cq, ph[0]);
+                tc::tmem_ld8(tm_d1 + 64 * buf + ((uint32_t)(32 * lq) << 16) + 32 + 8 * cq, ph[1]);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(d1_empty + buf);
+                if (tid == 0) TL(t, 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float c8[8], s8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool live = (c0 + 32 * h + 8 * cq + i) < a.M;
+                        const float x = ph[h][i] + bias;
+                        if (rbf) {
+                            float sn, cs;
+                            sincos_cw(x, &sn, &cs);
+                            c8[i] = live ? scale * cs : 0.f;
+                            s8[i] = live ? scale * sn : 0.f;
+                        } else {
+                            c8[i] = live ? scale * fmaxf(x, 0.f) : 0.f;
+                        }
+                    }
+                    if (tid == 0 && h == 1) TL(t, 2);
+                    const int u = 2 * t + h, q = u % 3;
+                    uint8_t* sub = sPhi + q * 2 * V2_BLK;             // [cos block | sin block] of sub-tile u
+                    tc::mbar_wait(phi_empty + q, ((u / 3) & 1) ^ 1);  // GEMM #2 and the store of the sub-tile last held here are done
+                    if (tid == 0 && h == 1) TL(t, 3);
+#pragma unroll
+                    for (int c4 = 0; c4 < 2; ++c4) {
+                        *reinterpret_cast<float4*>(sub + tc::sw128_chunk(r, 2 * cq + c4)) =
+                            make_float4(c8[4 * c4], c8[4 * c4 + 1], c8[4 * c4 + 2], c8[4 * c4 + 3]);
+                        if (rbf)
+                            *reinterpret_cast<float4*>(sub + V2_BLK + tc::sw128_chunk(r, 2 * cq + c4)) =
+                                make_float4(s8[4 * c4], s8[4 * c4 + 1], s8[4 * c4 + 2], s8[4 * c4 + 3]);
+                    }
+                    tc::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(phi_full + q);
+                }
+                if (tid == 0) TL(t, 4);
+                continue;
+            }
             float p[16];
             tc::tmem_ld16(tm_d1 + 64 * buf + ((uint32_t)(32 * lq) << 16) + 16 * cq, p);
             tc::tmem_ld_wait();
@@ -397,30 +459,38 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                 if (lane == 0) TL(t, 6);
             }
         } else if (KRING) {
-            // A in tensor memory, z k-blocks from the ring: 12 UMMAs per k-block, the slot is released as soon as they retire
-            int it = 0;
+            // A in tensor memory, z k-blocks from the ring: 12 UMMAs per k-block, the slot is released as soon as they retire.
+            // The k-block loop is unrolled with a compile-time kb (A columns and descriptor offsets are immediates, the ring
+            // slot is one add per k-block) and the slot / phase are carried, not recomputed: with a runtime kb the issue of a
+            // tile's 48 UMMAs took 3.7 k cycles (uniform-datapath arithmetic in front of every instruction) and bounded the
+            // kernel once the sub-tile ring had taken the store off the critical path.
+            int slot = 0;
+            uint32_t ph = 0;
             for (int t = 0; t < n_my; ++t) {
                 const int buf = t & 1;
                 tc::mbar_wait(d1_empty + buf, ((t >> 1) & 1) ^ 1);
                 if (lane == 0) TL(t, 5);
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const int slot = it % NS1;
-                    tc::mbar_wait(b1_full + slot, (it / NS1) & 1);
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
-                        const uint64_t dzh = dB1 + ((slot * b1_stage) >> 4), dzl = dzh + (V2_BBLK >> 4);
-                        const uint32_t dcol = tm_d1 + 64 * buf;
+                const uint32_t dcol = tm_d1 + 64 * buf;
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint32_t acol = 32 * kb + 8 * k4;
-                            tc::umma_tf32_ts(dcol, tm_alo + acol, dzh + 2 * k4, IDESC1, (kb | k4) != 0 ? 1u : 0u);
-                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dzl + 2 * k4, IDESC1, 1u);
-                            tc::umma_tf32_ts(dcol, tm_ahi + acol, dzh + 2 * k4, IDESC1, 1u);
+                for (int kb = 0; kb < V2_KB; ++kb) {
+                    if (kb < n_kb) {
+                        tc::mbar_wait(b1_full + slot, ph);
+                        tc::tc_fence_after();
+                        if (tc::elect_one()) {
+                            const uint64_t dzh = dB1 + (uint32_t)(slot * (int)((2 * V2_BBLK) >> 4)), dzl = dzh + (V2_BBLK >> 4);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const uint32_t acol = 32 * kb + 8 * k4;
+                                tc::umma_tf32_ts(dcol, tm_alo + acol, dzh + 2 * k4, IDESC1, (kb | k4) != 0 ? 1u : 0u);
+                                tc::umma_tf32_ts(dcol, tm_ahi + acol, dzl + 2 * k4, IDESC1, 1u);
+                                tc::umma_tf32_ts(dcol, tm_ahi + acol, dzh + 2 * k4, IDESC1, 1u);
+                            }
+                            tc::umma_commit(b1_empty + slot);              // k-block consumed
+                            if (kb == n_kb - 1) tc::umma_commit(d1_full + buf);   // P ready
                         }
-                        tc::umma_commit(b1_empty + slot);              // k-block consumed
-                        if (kb == n_kb - 1) tc::umma_commit(d1_full + buf);   // P ready
+                        __syncwarp();
+                        if (++slot == NS1) { slot = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
                 }
                 if (lane == 0) TL(t, 6);
             }
@@ -452,6 +522,30 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
         // ===================================== MMA-2 ISSUER =====================================
         const uint64_t dPhi = tc::make_desc_sw128(tc::smem_u32(sPhi));
         const uint64_t dW = tc::make_desc_sw128(tc::smem_u32(sW));
+        if (SUB3) {
+            // sub-tile u = 2 t + h: A = its [cos | sin] blocks, B = W^T blocks h (cos rows) and 2 + h (sin rows) of tile t's stage
+            for (int u = 0; u < 2 * n_my; ++u) {
+                const int t = u >> 1, h = u & 1, q = u % 3, ws = t % NSW;
+                tc::mbar_wait(phi_full + q, (u / 3) & 1);
+                if (a.do_gemm2 && h == 0) tc::mbar_wait(w_full + ws, (t / NSW) & 1);
+                if (lane == 0 && h == 0) TL(t, 7);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    if (a.do_gemm2) {
+                        // straight-line issue (compile-time block / k offsets, constant accumulate flags; see issue_gemm1)
+                        const uint64_t dw_h = dW + (uint32_t)(((ws * 4 + h) * NG * 128) >> 4);
+                        const uint64_t dphi = dPhi + (uint32_t)((q * 2 * V2_BLK) >> 4);
+                        if (rbf) issue_gemm2_sub<2, NG>(tm_d2, dphi, dw_h, IDESC2, u != 0 ? 1u : 0u);
+                        else issue_gemm2_sub<1, NG>(tm_d2, dphi, dw_h, IDESC2, u != 0 ? 1u : 0u);
+                        if (h == 1) tc::umma_commit(w_empty + ws);
+                    }
+                    tc::umma_commit(phi_empty + q);        // sub-tile consumed by the tensor core (1 of 2 arrivals)
+                    if (u == 2 * n_my - 1) tc::umma_commit(d2_full);
+                }
+                __syncwarp();
+                if (lane == 0 && h == 1) TL(t, 8);
+            }
+        } else
         for (int u = 0; u < n_my; ++u) {
             const int ws = u % NSW;
             const int pbuf = u % NPHI;
@@ -531,6 +625,33 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
         // ===================================== STORE WARP =====================================
         if (tc::elect_one()) {
             const bool storing = a.Phi != nullptr && !direct_store && !reg_store;
+            if (SUB3) {
+                for (int u = 0; u < 2 * n_my; ++u) {
+                    const int t = u >> 1, h = u & 1, q = u % 3;
+                    const int c0 = (ct0 + t) * V2_BN;
+                    tc::mbar_wait(phi_full + q, (u / 3) & 1);
+                    if (storing) {
+                        const uint8_t* sub = sPhi + q * 2 * V2_BLK;
+                        if (a.phi_blocked) {
+                            const int nb = rbf ? 4 : 2;
+                            const int blk0 = ((int)blockIdx.x * n_ct + (ct0 + t)) * nb;
+                            tc::tma_store_3d(&map_cos, tc::smem_u32(sub), 0, (blk0 + h) * V2_BM, chain);
+                            if (rbf) tc::tma_store_3d(&map_cos, tc::smem_u32(sub + V2_BLK), 0, (blk0 + 2 + h) * V2_BM, chain);
+                        } else if (c0 + 32 * h < a.M) {
+                            tc::tma_store_3d(&map_cos, tc::smem_u32(sub), c0 + 32 * h, row0, chain);
+                            if (rbf) tc::tma_store_3d(&map_sin, tc::smem_u32(sub + V2_BLK), c0 + 32 * h, row0, chain);
+                        }
+                        tc::tma_commit();
+                        if (u > 0) {
+                            tc::tma_wait_read1();                  // the store of sub-tile u-1 has read its buffer; u's is in flight
+                            tc::mbar_arrive(phi_empty + ((u - 1) % 3));
+                        }
+                    } else {
+                        tc::mbar_arrive(phi_empty + q);
+                    }
+                }
+                tc::tma_wait0();
+            } else
             for (int t = 0; t < n_my; ++t) {
                 const int c0 = (ct0 + t) * V2_BN;
                 const int pbuf = t % NPHI;
@@ -564,7 +685,7 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                     tc::mbar_arrive(phi_empty + pbuf);
                 }
             }
-            tc::tma_wait0();
+            if (!SUB3) tc::tma_wait0();
         }
     }
     tc::tc_fence_before();
@@ -761,13 +882,30 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     // (with the register-store experiment no TMA store sits on the tile's critical path: one Phi tile and two whole-tile z
     //  stages, as in the eval-mode forward)
     const bool regst = a.phi_blocked && getenv("DGPRF_TC2_REG_STORE");
+    // Default when the features are stored: THREE Phi sub-tile buffers (96 KB) + as many k-block slots as fit (six with
+    // n_gp <= 32) -- the store of a sub-tile drains under the epilogue of the next two and GEMM #1 stays 1.5 tiles ahead.
+    // Tried on top of it and measured slower or equal at configs[4] layer scale (0.54 ms): W^T tiles loaded by the GEMM #2
+    // warp (blocking on the retirement of GEMM #2: 0.54; one tile later: 0.64; three W stages + five z slots: 0.54), by
+    // polling from the producer (0.69: the z stream falls behind with five slots), and forcing the issue order
+    // G1(t+1), G2(t), G1(t+2) through a barrier between the two issuing threads (0.55-0.60).  What bounds a tile now is the
+    // in-order tensor pipe: GEMM #2 of tile t retires behind the GEMM #1 work queued in front of it, and its commit is what
+    // frees a Phi sub-tile buffer and a W stage.
+    // DGPRF_TC2_NO_SUB3=1 gives round 2's earlier geometry back (two whole Phi tiles + four slots for <= 3 k-blocks, one Phi
+    // tile + two whole-tile z stages otherwise).
+    const size_t smem_fix3 = 1024 + V2_HDR + 6 * (size_t)V2_BLK + 2 * 4 * (size_t)NG * 128;
+    int sub3_slots = (a.Phi != nullptr && !regst && !phi2 && !e_kr && !getenv("DGPRF_TC2_NO_SUB3") && !getenv("DGPRF_TC2_DIRECT_STORE"))
+                         ? (int)((232448 - (long long)smem_fix3) / (2 * V2_BBLK)) : 0;
+    if (sub3_slots > 6) sub3_slots = 6;
+    const bool sub3 = sub3_slots >= 3 && sub3_slots > n_kb;
     int kring = a.Phi == nullptr ? 0 : (e_kr ? atoi(e_kr) : ((n_kb <= 3 && !regst) ? 4 : 0));
     if (kring > 6) kring = 6;
     const int nsw_k = getenv("DGPRF_TC2_NSW") ? atoi(getenv("DGPRF_TC2_NSW")) : 2;      // W^T ring stages next to the k-block ring (1 | 2)
     const size_t smem_kring = 1024 + V2_HDR + 8 * (size_t)V2_BLK + (size_t)(nsw_k == 1 ? 1 : 2) * 4 * (size_t)NG * 128 + (size_t)kring * 2 * V2_BBLK;
     if (kring < 2 || smem_kring > 232448) kring = 0;
+    if (sub3) kring = sub3_slots;
     const int ns1 = kring ? kring : (phi2 ? 1 : (tc2_smem_bytes(NG, n_kb, 2) <= 232448 ? 2 : 1));
-    const size_t smem = kring ? smem_kring : tc2_smem_bytes(NG, n_kb, ns1) + (phi2 ? 4 * (size_t)V2_BLK : 0);
+    const size_t smem = sub3 ? smem_fix3 + (size_t)kring * 2 * V2_BBLK
+                             : (kring ? smem_kring : tc2_smem_bytes(NG, n_kb, ns1) + (phi2 ? 4 * (size_t)V2_BLK : 0));
     { const int rc_s = dgprf_ensure_smem((const void*)k1_fwd_tc2<NG, false>, (size_t)232448); if (rc_s) return rc_s; }
     DGPRF_REQUIRE(a.zt != nullptr && a.wt != nullptr, "pipelined forward needs the prepped operand buffers");
     if (!a.prepped) {
@@ -796,7 +934,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, (16 * 12 + 8) * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, (16 * 12 + 8) * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0) | ((tl && getenv("DGPRF_TC2_TIMELINE_RB")) ? (atoi(getenv("DGPRF_TC2_TIMELINE_RB")) << 16) : 0), tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && !sub3 && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (sub3 ? 0x1000 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0) | ((tl && getenv("DGPRF_TC2_TIMELINE_RB")) ? (atoi(getenv("DGPRF_TC2_TIMELINE_RB")) << 16) : 0), tl, mc, ms, mz, mw, mw); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12 + 8];
