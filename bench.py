@@ -152,7 +152,7 @@ def algorithmic_flops(spec, B):
 
 
 # ncu --set full captures of the dominant kernel on THIS workload (profiles/r02_ncu_summary.md): DRAM bytes per launch
-NCU_TRAFFIC = {"k10_": (290048.0, "profiles/r02_ncu_k10_raw.csv"), "k9_": (408576.0, "profiles/r01_ncu_full_summary.md section E")}
+NCU_TRAFFIC = {"k10_": (290816.0, "profiles/r02_ncu_k10_final_raw.csv"), "k9_": (408576.0, "profiles/r01_ncu_full_summary.md section E")}
 
 CFG4 = dict(workload="configs[3]: 3-layer RBF RF-DGP on the synthetic YearPrediction shape, 8 chains per GPU batched per launch, "
                      "sharded predictive averaging", N=515345, D=90, L=3, n_rf=512, n_gp=[30, 30, 1], input_cat=True,
@@ -427,8 +427,8 @@ def run_ours(args, rank, world):
                 "kernel": f'{dom["kernel"]} ({dom["what"]})', "avg_us": dom["avg_us"],
                 "peak_source": "cuBLAS TF32 matmul 8192^3 measured live in this run (best of 10)",
                 "binding_resource": "issue slots / dependent-phase latency, NOT the tensor pipe: configs[1] is 0.18 GFLOP and 0.4 MB of "
-                                    "parameters per step; ncu (profiles/r02_ncu_summary.md): tensor pipe 13 % active (legacy mma.sync tf32 "
-                                    "measures 1024 FLOP/clk/SM on B200, a third of that with the 3xTF32 split), issue slots 46 %, 16 warps/SM",
+                                    "parameters per step; ncu (profiles/r02_ncu_summary.md): tensor pipe 14 % active (legacy mma.sync tf32 "
+                                    "measures 1024 FLOP/clk/SM on B200, a third of that with the 3xTF32 split), issue slots 44 %, 16 warps/SM",
                 "note": "roofline_tc_layer and roofline_k5_256MiB in this line give the tcgen05 and update kernels at throughput-relevant sizes"}
     else:
         ach = dom["bytes"] / (dom["avg_us"] * 1e-6) / 1e9
@@ -531,10 +531,13 @@ def run_ours(args, rank, world):
         "workload": f"one [RF->GP] layer at configs[4] scale: B={tB}, d={td}, M={tM}, n_gp={tg}, RBF, tf32 mode",
         "tf32_peak_tflops": tf32_peak, "tf32_peak_source": "cuBLAS TF32 matmul 8192^3, measured live (best of 10)",
         "hbm_copy_peak_gbs": pk["hbm_gbs"],
-        "traffic_ncu_bytes": {"fwd": 2.104e9 + 84.0e6, "bwd": 2.166e9 + 4.2e6, "algorithmic_phi_bytes": phi_bytes,
-                              "source": "ncu --set full, profiles/r01_ncu_full_summary.md section E"},
+        "traffic_ncu_bytes": {"fwd": 2.105e9 + 84.0e6, "bwd": 2.173e9 + 63.1e6, "algorithmic_phi_bytes": phi_bytes,
+                              "source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of layer 1 of a 3-layer configs[4]-shaped "
+                                        "model (same tile shapes; the backward also writes the dF slabs of the layer below): "
+                                        "profiles/r02_ncu_summary.md, profiles/r02_ncu_tc_final_raw.csv"},
         "fwd": tc_entry("k1_fwd_tc2", 2.0 * tB * (td * tM + tF * tg), 2.0 * tB * (3 * 128 * tM + tF * tg),
-                        "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored (TMA): bound by the write stream"),
+                        "3xTF32 phase GEMM (A in TMEM) + sincos epilogue + Phi.W; Phi stored by TMA as 32-column sub-tiles through a ring of three "
+                        "buffers (tile-blocked layout in HBM); bound by the in-order tensor pipe + the TMA store, see profiles/r02_summary.md"),
         "bwd": tc_entry("k2_bwd_tc2", 4.0 * tB * tF * tg, 4.0 * tB * tF * 32,
                         "dPhi = dF.W^T, gW += Phi^T.dF (accumulators resident in TMEM); Phi loaded (TMA ring)"),
     }
