@@ -23,8 +23,17 @@
 #include "tc_common.cuh"
 
 constexpr int B2_BM = 128, B2_BN = 64, B2_NG = 32;
-constexpr int B2_EPI_WARPS = 8;
-constexpr int B2_THREADS = (B2_EPI_WARPS + 2) * 32;     // 8 epilogue warps + the MMA issuer warp + the TMA producer warp
+// Epilogue warps: 8 (a warp owns 32 rows x 32 tile columns) or 16 (32 rows x 16 columns; -DB2_EW=16).  Measured at configs[4]
+// scale: 16 warps are no faster (65 536 rows: 528-543 us per layer against 513-527; 8 192 rows: 86-88 against 88-93) -- the
+// per-tile chain is the waits (Phi arrival, dPhi, dP consumed) and shared-memory bandwidth, not the warps' instruction count.
+#ifndef B2_EW
+#define B2_EW 8
+#endif
+constexpr int B2_EPI_WARPS = B2_EW;
+constexpr int B2_CQ = B2_EPI_WARPS / 4;        // column groups of a tile (2 x 32 | 4 x 16 columns)
+constexpr int B2_CW = B2_BN / B2_CQ;           // tile columns per epilogue thread
+constexpr int B2_NCH = B2_CW / 4;              // 16-byte chunks per epilogue thread and half (cos | sin)
+constexpr int B2_THREADS = (B2_EPI_WARPS + 2) * 32;     // epilogue warps + the MMA issuer warp + the TMA producer warp
 constexpr int B2_BLK = B2_BM * 128;            // bytes of a [128 x 32 tf32] block
 constexpr int B2_HDR = 2048;                   // R_s | s_s | m_s | mbarriers | TMEM slot
 constexpr int B2_MAX_LOC = 10;                 // resident gW tiles: 10 x 32 TMEM columns
@@ -51,8 +60,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
            const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_z) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* R_s = reinterpret_cast<float*>(sm);                 // [2][128] row sums of dP per column half
-    float* s_s = R_s + 2 * B2_BM;                              // [64] exp(log_inv_ls[q]), q < d_prev
+    float* s_s = reinterpret_cast<float*>(sm) + 2 * B2_BM;     // [64] exp(log_inv_ls[q]), q < d_prev  (the first 1 KB is unused)
     float* m_s = s_s + 64;                                     // [64] mean[q]
     uint64_t* bars = reinterpret_cast<uint64_t*>(m_s + 64);
     uint64_t* phi_full = bars + 0;    // [2] TMA complete_tx
@@ -73,6 +81,8 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
     uint8_t* sdF = sPhi + 2 * 4 * B2_BLK;            // [128 rows x 32 j]  K-major, 16-byte-atom swizzle (A of MMA-1)
     uint8_t* sdF2 = sdF + B2_BLK;                    // the same tile, MN-major 32-byte-atom swizzle (B of MMA-2)
     uint8_t* sdP = sdF2 + B2_BLK;                    // 2 blocks [128 rows x 32 feature cols]          (A of MMA-3)
+    float* R_s = reinterpret_cast<float*>(sdP);      // [B2_CQ][128] row sums of dP per column group: ALIASES the dP tile, only
+                                                     // touched at a row end between "MMA-3 of the last tile retired" and the next dP
     uint8_t* sW = sdP + 2 * B2_BLK;                  // [128 feature rows x 32 j]                      (B of MMA-1)
     uint8_t* sZ = sW + B2_BLK;                       // 2 blocks [64 q rows x 32 feature cols]         (B of MMA-3)
 
@@ -226,6 +236,25 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                     if (rbf) tc::tma_load_3d(&map_sin, tc::smem_u32(sPhi + (s * 4 + 2 + b) * B2_BLK), phi_full + s, c0 + 32 * b, row0, chain);
                 }
             };
+            // DGPRF_BWD_PF=<n> (A/B switch, off by default): L2 prefetch of the saved-feature tile n tiles ahead of the ring.  The idea:
+            // the two 64 KB stages keep ~64 KB in flight per SM and a tile takes ~4 k cycles to arrive, while the same load from
+            // L2 takes < 1 k (profiles/r02_tma_load_rate.txt: 72-120 B / clk / SM for tiled and bulk loads alike).  Measured at
+            // configs[4] scale: monotonically SLOWER, 507 -> 554 / 537 / 568 / 575 / 626 us per layer for n = 1 / 2 / 3 / 4 / 6
+            // (profiles/r02_bwd_prefetch.txt) -- the prefetches queue in front of the W / z / Phi loads the next tile waits for.
+            auto prefetch_phi = [&](int k) {
+                if (k >= T) return;
+                if (a.phi_blocked) {
+                    const int nb = rbf ? 4 : 2;
+                    const int blk0 = ((rs + (k / n_loc) * a.RS) * n_ct + (cs + (k % n_loc) * a.CS)) * nb;
+                    for (int b = 0; b < nb; ++b) tc::tma_prefetch_3d(&map_cos, 0, (blk0 + b) * B2_BM, chain);
+                } else {
+                    const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN, row0 = (rs + (k / n_loc) * a.RS) * B2_BM;
+                    for (int b = 0; b < 2; ++b) {
+                        tc::tma_prefetch_3d(&map_cos, c0 + 32 * b, row0, chain);
+                        if (rbf) tc::tma_prefetch_3d(&map_sin, c0 + 32 * b, row0, chain);
+                    }
+                }
+            };
             auto load_w = [&](int k) {
                 const int c0 = (cs + (k % n_loc) * a.CS) * B2_BN;
                 tc::mbar_expect_tx(w_full, (rbf ? 2u : 1u) * (B2_BN * 128));
@@ -239,6 +268,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             };
             load_phi(0);
             if (T > 1) load_phi(1);
+            for (int i = 0; i < pf_dist; ++i) prefetch_phi(2 + i);
             load_w(0);
             if (NQ > 0) load_z(0, 0);
             for (int k = 0; k < T; ++k) {
@@ -253,6 +283,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                     tc::mbar_wait((k & 1) ? e_read1 : e_read, (k >> 1) & 1);
                     tc::mbar_wait((k & 1) ? barC1 : barC, (k >> 1) & 1);
                     load_phi(k + 2);
+                    if (pf_dist > 0) prefetch_phi(k + 2 + pf_dist);
                 }
                 TLB(k, 8);
                 if (NQ > 0 && k + 1 < T) {                          // MMA-3(k) done: the z tile is free for tile k+1
@@ -264,7 +295,8 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
         __syncwarp();
     } else {
         // ============================================ EPILOGUE ============================================
-        const int lq = warp & 3, hh = warp >> 2;             // TMEM lane quarter, 32-column half of the tile
+        const int lq = warp & 3, hh = warp >> 2;             // TMEM lane quarter, column group of the tile (B2_CW columns)
+        const int pblk = (hh * B2_CW) >> 5, pch = ((hh * B2_CW) & 31) >> 2;    // 32-column Phi / dP block and first 16-byte chunk in it
         const int r = 32 * lq + lane;
         float rsum = 0.f;
         constexpr int ET = B2_EPI_WARPS * 32;
@@ -312,19 +344,19 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             //      release barrier per stage: its next phase needs the stage's next TMA load, which the issuer only
             //      requests after consuming this phase, so it can never run two phases ahead of the issuer's wait ----
             const uint8_t* ph = sPhi + s * 4 * B2_BLK;
-            float4 pcv[8], psv[8];
+            float4 pcv[B2_NCH], psv[B2_NCH];
             // In the 32-byte-atom layout the 16-byte chunk cc of row r sits at unit (cc/2) ^ (r & 3), half cc & 1: at a fixed
             // cc the 32 rows of a warp only touch 4 of the 8 16-byte bank groups.  Rows with (r >> 2) & 1 read the two
             // halves of each unit in the opposite order (then swap the registers back), which covers all 8 groups.
             const int hsw = (r >> 2) & 1;
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                pcv[cc] = *reinterpret_cast<const float4*>(ph + hh * B2_BLK + tc::sw128b32_chunk(r, cc ^ hsw));
-                if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + hh) * B2_BLK + tc::sw128b32_chunk(r, cc ^ hsw));
+            for (int cc = 0; cc < B2_NCH; ++cc) {
+                pcv[cc] = *reinterpret_cast<const float4*>(ph + pblk * B2_BLK + tc::sw128b32_chunk(r, pch + (cc ^ hsw)));
+                if (rbf) psv[cc] = *reinterpret_cast<const float4*>(ph + (2 + pblk) * B2_BLK + tc::sw128b32_chunk(r, pch + (cc ^ hsw)));
             }
             if (hsw) {
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) {
+                for (int j = 0; j < B2_NCH; j += 2) {
                     const float4 t = pcv[j]; pcv[j] = pcv[j + 1]; pcv[j + 1] = t;
                     if (rbf) { const float4 u = psv[j]; psv[j] = psv[j + 1]; psv[j + 1] = u; }
                 }
@@ -336,14 +368,13 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             if (tid == 0) TLB(k, 2);
             tc::tc_fence_after();
             // ---- dPhi of the thread's row x 32 columns -> registers, then D1 is free for MMA-1 of the next tile ----
-            float dcv[32], dsv[32];
+            float dcv[B2_CW], dsv[B2_CW];
             {
                 const uint32_t lane_addr = (uint32_t)(32 * lq) << 16;
-                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh, dcv);
-                tc::tmem_ld16(tm_d1 + lane_addr + 32 * hh + 16, dcv + 16);
-                if (rbf) {
-                    tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh, dsv);
-                    tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + 32 * hh + 16, dsv + 16);
+#pragma unroll
+                for (int c16 = 0; c16 < B2_CW / 16; ++c16) {
+                    tc::tmem_ld16(tm_d1 + lane_addr + B2_CW * hh + 16 * c16, dcv + 16 * c16);
+                    if (rbf) tc::tmem_ld16(tm_d1 + lane_addr + B2_BN + B2_CW * hh + 16 * c16, dsv + 16 * c16);
                 }
                 tc::tmem_ld_wait();
             }
@@ -355,7 +386,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             if (tid == 0) TLB(k, 4);
             // ---- dP -> dP tile (A of MMA-3), row sums ----
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {                  // 16-byte chunk inside the 32-wide block
+            for (int cc = 0; cc < B2_NCH; ++cc) {             // 16-byte chunks of this thread inside its 32-wide block
                 const float4 pc = pcv[cc];
                 const float* dc = dcv + 4 * cc;
                 float4 o;
@@ -374,7 +405,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                 }
                 rsum += (o.x + o.y) + (o.z + o.w);
                 o.x = tc::tf32_rn_bits(o.x); o.y = tc::tf32_rn_bits(o.y); o.z = tc::tf32_rn_bits(o.z); o.w = tc::tf32_rn_bits(o.w);
-                *reinterpret_cast<float4*>(sdP + hh * B2_BLK + tc::sw128_chunk(r, cc)) = o;
+                *reinterpret_cast<float4*>(sdP + pblk * B2_BLK + tc::sw128_chunk(r, pch + cc)) = o;
             }
             tc::tc_fence_before();
             tc::fence_async_smem();
@@ -383,14 +414,16 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
             if (tid == 0) TLB(k, 5);
             if (row_end) {
                 // ---- end of the row tile: dF_prev slab = s*T + mean*R, written once ----
+                tc::mbar_wait(barB, k & 1);                    // T = sum over the row tile's column tiles is final (and the dP tile is idle)
+                tc::tc_fence_after();
                 R_s[hh * B2_BM + r] = rsum;
                 rsum = 0.f;
-                tc::mbar_wait(barB, k & 1);                    // T = sum over the row tile's column tiles is final
-                tc::tc_fence_after();
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s complete
+                asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");  // R_s complete
                 if (warp < 4) {
                     const int64_t row = row0 + r;                          // warp < 4: r = 32 * warp + lane
-                    const float Rr = R_s[r] + R_s[B2_BM + r];
+                    float Rr = R_s[r];
+#pragma unroll
+                    for (int c = 1; c < B2_CQ; ++c) Rr += R_s[c * B2_BM + r];
                     if (hyper && row < a.B) a.Rpart[chain * a.r_cs + (int64_t)cs * a.B + row] = Rr;
                     for (int qc = 0; qc < NQ / 16; ++qc) {
                         float t[16];
@@ -413,7 +446,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                     }
                 }
                 tc::tc_fence_before();
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // R_s and D3 are read: the next row tile may reuse them
+                asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");  // R_s and D3 are read: the next row tile may reuse them
                 if (k + 1 < T) {
                     // its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
                     tc::mbar_wait((k & 1) ? barC1 : barC, (k >> 1) & 1);
@@ -440,7 +473,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                         for (int j = 0; j < 16; ++j) stg[fl * 33 + 16 * c16 + j] = T > 0 ? v[j] : 0.f;
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");
                 const int c0 = (cs + i * a.CS) * B2_BN;
                 const int ncol = min(B2_BN, a.M - c0);                     // live feature columns of this tile
                 float* base = a.gWpart + chain * a.gw_cs + (int64_t)rs * a.gw_ss;
@@ -451,7 +484,7 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                         dst[e] = stg[(half * B2_BN + f) * 33 + j];
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");
             }
         }
     }
