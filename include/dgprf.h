@@ -19,6 +19,10 @@
  *     floats; stride 0 shares the operand between chains.
  *   - no CPU fallback: without a CUDA device every compute entry point fails with
  *     DGPRF_ECUDA.
+ *   - no model state is kept between calls.  What IS remembered, per thread, are plans
+ *     that are pure functions of the arguments (the last workspace layout, the last
+ *     step-kernel geometry and argument block), keyed by the model description, the
+ *     batch size, the mode and a signature of the process environment.
  */
 #ifndef DGPRF_H
 #define DGPRF_H
