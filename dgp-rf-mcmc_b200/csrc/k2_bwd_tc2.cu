@@ -45,6 +45,9 @@ __device__ __forceinline__ void mbar_arrive_b2(uint64_t* bar) {
 }
 }  // namespace tc
 
+// (Measured and not kept, round 2: a third single-thread role issuing MMA-2 the moment a saved-feature tile lands instead of
+// inside the main issuer's loop -- 535-547 us per configs[4] layer against 507-523; sixteen epilogue warps; an L2 prefetch
+// ahead of the ring; the next row tile's dF loaded a tile early.  profiles/r02_summary.md section F.)
 // Roles: warps 0-7 = epilogue (dF staging, dP, dF_prev, gW write-out); warp 8 = MMA issuer (one elected thread issues every
 // UMMA); warp 9 = TMA producer (one elected thread issues every load).  Two single-thread roles because each mbarrier
 // wait costs a few hundred cycles even when it is already complete: one thread doing all nine waits of a tile took ~4000
