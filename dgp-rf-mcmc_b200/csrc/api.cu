@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.cuh"
 
 static thread_local char g_err[512] = "";
@@ -28,6 +29,14 @@ uint64_t dgprf_env_signature(void) {
     if (environ)
         for (char** e = environ; *e; ++e) h = (h ^ (uint64_t)(uintptr_t)*e) * 0x100000001b3ull;
     return h;
+}
+
+bool dgprf_pdl_enabled() {
+    static thread_local uint64_t env = 0;
+    static thread_local bool on = true, known = false;
+    const uint64_t e = dgprf_env_signature();
+    if (!known || e != env) { on = getenv("DGPRF_NO_PDL") == nullptr; env = e; known = true; }
+    return on;
 }
 
 // ---- per-(kernel, device) shared-memory opt-in -------------------------------------------------

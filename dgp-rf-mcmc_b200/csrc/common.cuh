@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include "../../include/dgprf.h"
 
 #define DGPRF_LOG_2PI 1.8378770664093453f
@@ -39,6 +40,30 @@ int dgprf_ensure_smem(const void* kernel, size_t smem);
 // Signature of the process environment (api.cu): key of the per-thread plan caches, so that a debug switch set or cleared
 // between two calls is seen by the next call.
 uint64_t dgprf_env_signature(void);
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// The kernels of a layered step (operand prep, forward, slab sums, likelihood, backward, finalize, update: ~15-25 dependent
+// launches) are launched with programmatic stream serialization: the next grid is scheduled while the previous one still
+// runs and blocks in griddepcontrol.wait -- the FIRST instruction of every kernel of this library -- until that grid has
+// completed and its writes are visible.  Nothing is ever touched early, so the only overlap is the launch latency and block
+// scheduling (2-3 us per dependent launch), which is what a small layered step is made of.  A kernel launched without the
+// attribute, or after a kernel that never signals, behaves exactly as before.  DGPRF_NO_PDL=1 switches the attribute off.
+__device__ __forceinline__ void dgprf_pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool dgprf_pdl_enabled();       // api.cu (reads the environment through the per-thread signature cache)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dgprf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = dgprf_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1)
 k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, const __grid_constant__ CUtensorMap map_cos,
            const __grid_constant__ CUtensorMap map_sin, const __grid_constant__ CUtensorMap map_zt, const __grid_constant__ CUtensorMap map_wt,
            const __grid_constant__ CUtensorMap map_at) {
+    dgprf_pdl_sync();
     // NSW_ bit 8 (DGPRF_TC2_DIRECT_STORE=1, an experiment kept for A/B runs): the epilogue warps store the saved features
     // straight from registers (st.global.v4, 64 B per row and half) instead of the store warp's TMA store of the shared
     // tile.  Measured at configs[4] layer scale: 1.39 ms against 0.65 ms -- a warp-wide store of 32 rows 32 KB apart is 32
@@ -736,6 +737,7 @@ k_prep_tc2(const float* __restrict__ z, int64_t z_cs, int d, int M, float* __res
 // at [2][B][Kp]: the layer input (previous layer's output slabs summed in slab order | model input), tf32 hi / lo, zero padded
 __global__ void __launch_bounds__(256)
 k_prep_wide_a(const FwdArgs a, int Kp, float* __restrict__ at) {
+    dgprf_pdl_sync();
     // grid (row blocks of 8 rows, chains); a thread converts 4 consecutive K columns of one row per step (float4 stores)
     const int chain = blockIdx.y;
     const int64_t n = (int64_t)a.B * Kp;
@@ -838,7 +840,7 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
         ProfScope _ps("k_prep_tc2_wide", st);
         int blocks = ceil_div(a.B, 8);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        k_prep_wide_a<<<dim3(blocks, n_chains), 256, 0, st>>>(a, Kp, a.at);
+        DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_prep_wide_a, dim3(blocks, n_chains), dim3(256), 0, st, a, Kp, a.at));
         if (!a.prepped) {
             k_prep_wide_o<<<dim3(ceil_div(a.M, 32), Kp / 32, n_chains), 256, 0, st>>>(a, Kp, a.ot);
             const int n_wt_tiles = ceil_div(a.F, 32) * ceil_div(NG, 32);
@@ -861,7 +863,7 @@ static int launch_fwd_tc2_wide(const FwdArgs& a, int n_chains, cudaStream_t st) 
     if (rc) return rc;
     static long long* tl = nullptr;
     dim3 grid(ceil_div(a.B, V2_BM), a.CS, n_chains);
-    { ProfScope _ps("k1_fwd_tc2_wide", st); k1_fwd_tc2<NG, true><<<grid, V2_THREADS, smem, st>>>(a, ns, nsw | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0), tl, mc, ms, mo, mw, ma); }
+    { ProfScope _ps("k1_fwd_tc2_wide", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k1_fwd_tc2<NG, true>, grid, dim3(V2_THREADS), smem, st, a, ns, nsw | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0), tl, mc, ms, mo, mw, ma)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -934,7 +936,7 @@ static int launch_fwd_tc2(const FwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_TC2_TIMELINE") && !tl) { cudaMalloc(&tl, (16 * 12 + 8) * sizeof(long long)); }
     if (tl) cudaMemsetAsync(tl, 0, (16 * 12 + 8) * sizeof(long long), st);
-    { ProfScope _ps("k1_fwd_tc2", st); k1_fwd_tc2<NG, false><<<grid, V2_THREADS, smem, st>>>(b, ns1, ((kring && !sub3 && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (sub3 ? 0x1000 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0) | ((tl && getenv("DGPRF_TC2_TIMELINE_RB")) ? (atoi(getenv("DGPRF_TC2_TIMELINE_RB")) << 16) : 0), tl, mc, ms, mz, mw, mw); }
+    { ProfScope _ps("k1_fwd_tc2", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k1_fwd_tc2<NG, false>, grid, dim3(V2_THREADS), smem, st, b, ns1, ((kring && !sub3 && nsw_k == 1) ? 1 : 2) | (getenv("DGPRF_TC2_DIRECT_STORE") ? 0x100 : 0) | ((phi2 || kring) ? 0x200 : 0) | (kring ? 0x400 : 0) | (sub3 ? 0x1000 : 0) | (getenv("DGPRF_TC2_REG_STORE") ? 0x800 : 0) | ((tl && getenv("DGPRF_TC2_TIMELINE_RB")) ? (atoi(getenv("DGPRF_TC2_TIMELINE_RB")) << 16) : 0), tl, mc, ms, mz, mw, mw)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == (atoi(getenv("DGPRF_TC2_TIMELINE")) > 1 ? atoi(getenv("DGPRF_TC2_TIMELINE")) : 4)) {
         long long h[16 * 12 + 8];

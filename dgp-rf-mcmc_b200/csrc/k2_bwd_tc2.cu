@@ -61,6 +61,7 @@ __device__ __forceinline__ void mbar_arrive_b2(uint64_t* bar) {
 __global__ void __launch_bounds__(B2_THREADS, 1)
 k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid_constant__ CUtensorMap map_cos, const __grid_constant__ CUtensorMap map_sin,
            const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_z) {
+    dgprf_pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_s = reinterpret_cast<float*>(sm) + 2 * B2_BM;     // [64] exp(log_inv_ls[q]), q < d_prev  (the first 1 KB is unused)
@@ -581,7 +582,7 @@ int dgprf_launch_bwd_tc2(const BwdArgs& a, int n_chains, cudaStream_t st) {
     static int tl_calls = 0;
     if (getenv("DGPRF_BWD_TIMELINE") && !tl) cudaMalloc(&tl, 16 * 12 * sizeof(long long));
     if (tl) cudaMemsetAsync(tl, 0, 16 * 12 * sizeof(long long), st);
-    { ProfScope _ps("k2_bwd_tc2", st); k2_bwd_tc2<<<grid, B2_THREADS, kB2Smem, st>>>(a, getenv("DGPRF_BWD_PF") ? atoi(getenv("DGPRF_BWD_PF")) : 0, tl, mc, ms, mw, mz); }
+    { ProfScope _ps("k2_bwd_tc2", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k2_bwd_tc2, grid, dim3(B2_THREADS), kB2Smem, st, a, getenv("DGPRF_BWD_PF") ? atoi(getenv("DGPRF_BWD_PF")) : 0, tl, mc, ms, mw, mz)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (tl && ++tl_calls == atoi(getenv("DGPRF_BWD_TIMELINE"))) {
         long long h[16 * 12];

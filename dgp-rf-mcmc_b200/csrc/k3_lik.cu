@@ -12,6 +12,7 @@ constexpr int kLikThreads = 1024;
 constexpr int kMaxClasses = 64;
 
 __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
+    dgprf_pdl_sync();
     __shared__ float red[32];
     const int chain = blockIdx.y;
     const float* Y = a.Y + chain * a.y_cs;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kLikThreads) k3_loglik(const LikArgs a) {
 }
 
 __global__ void __launch_bounds__(64) k3_loglik_final(const LikArgs a, int nblk) {
+    dgprf_pdl_sync();
     const int chain = blockIdx.x;
     if (threadIdx.x == 0) {
         float t = 0.f, g = 0.f;
@@ -100,10 +102,10 @@ int dgprf_launch_loglik(const LikArgs& a, int n_chains, cudaStream_t st) {
         nblk = ceil_div(a.B, threads);
         if (nblk > 64) nblk = 64;
     }
-    { ProfScope _ps("k3_loglik", st); k3_loglik<<<dim3(nblk, n_chains), threads, 0, st>>>(a); }
+    { ProfScope _ps("k3_loglik", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k3_loglik, dim3(nblk, n_chains), dim3(threads), 0, st, a)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     if (nblk > 1 && (a.ll_sum || a.g_lik_log_var)) {
-        k3_loglik_final<<<n_chains, 64, 0, st>>>(a, nblk);
+        DGPRF_CHECK_CUDA(dgprf_launch_pdl(k3_loglik_final, dim3(n_chains), dim3(64), 0, st, a, nblk));
         DGPRF_CHECK_CUDA(cudaGetLastError());
     }
     return DGPRF_OK;

@@ -16,6 +16,7 @@
 // shuffle tree, so all slab loads of a vector are in flight at once and the result stays deterministic.
 template <int LPV>
 __global__ void __launch_bounds__(256) k5_sgmcmc_update(const UpdArgs a, const __grid_constant__ SegTable tab) {
+    dgprf_pdl_sync();
     const int chain = blockIdx.y;
     const float* grad = a.grad + chain * a.grad_cs;
     const int64_t n4 = a.n >> 2;
@@ -71,8 +72,8 @@ int dgprf_launch_update(const UpdArgs& a, const dgprf_segment* segs, int n_seg, 
     dim3 grid(blocks, n_chains);
     {
         ProfScope _ps("k5_sgmcmc_update", st);
-        if (lpv == 8) k5_sgmcmc_update<8><<<grid, 256, 0, st>>>(a, tab);
-        else k5_sgmcmc_update<1><<<grid, 256, 0, st>>>(a, tab);
+        if (lpv == 8) DGPRF_CHECK_CUDA(dgprf_launch_pdl(k5_sgmcmc_update<8>, grid, dim3(256), 0, st, a, tab));
+        else DGPRF_CHECK_CUDA(dgprf_launch_pdl(k5_sgmcmc_update<1>, grid, dim3(256), 0, st, a, tab));
     }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;

@@ -6,6 +6,7 @@
 
 // ---- dense = sum of slabs ------------------------------------------------------------------
 __global__ void k_sum_slabs(SlabMat m, int B, int ncol, float* out, int64_t out_cs) {
+    dgprf_pdl_sync();
     const int chain = blockIdx.y;
     const int64_t n = (int64_t)B * ncol;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
@@ -17,6 +18,7 @@ __global__ void k_sum_slabs(SlabMat m, int B, int ncol, float* out, int64_t out_
 template <typename T>
 __global__ void __launch_bounds__(256) k_sum_slabs_dense(const float* __restrict__ base, int64_t cs, int64_t ss, int n_slabs, int64_t n,
                                                          float* __restrict__ out, int64_t out_cs) {
+    dgprf_pdl_sync();
     const T* p = reinterpret_cast<const T*>(base + blockIdx.y * cs);
     T* o = reinterpret_cast<T*>(out + blockIdx.y * out_cs);
     const int64_t sst = ss / (int64_t)(sizeof(T) / sizeof(float));
@@ -53,12 +55,12 @@ int dgprf_launch_sum_slabs(const SlabMat& m, int B, int ncol, float* out, int64_
         const int64_t nv = v4 ? n / 4 : n;
         int blocks = (int)((nv + 255) / 256);
         if (blocks > 2368) blocks = 2368;
-        if (v4) k_sum_slabs_dense<float4><<<dim3(blocks, n_chains), 256, 0, st>>>(m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs);
-        else k_sum_slabs_dense<float><<<dim3(blocks, n_chains), 256, 0, st>>>(m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs);
+        if (v4) DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_sum_slabs_dense<float4>, dim3(blocks, n_chains), dim3(256), 0, st, m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs));
+        else DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_sum_slabs_dense<float>, dim3(blocks, n_chains), dim3(256), 0, st, m.ptr, m.cs, m.ss, m.n_slabs, nv, out, out_cs));
     } else {
         int blocks = ceil_div(n, 256);
         if (blocks > 1184) blocks = 1184;
-        k_sum_slabs<<<dim3(blocks, n_chains), 256, 0, st>>>(m, B, ncol, out, out_cs);
+        DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_sum_slabs, dim3(blocks, n_chains), dim3(256), 0, st, m, B, ncol, out, out_cs));
     }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
@@ -83,6 +85,7 @@ int dgprf_launch_sum_rows(const float* in, int64_t in_cs, int n, float* out, int
 __global__ void k_grad_finalize(const float* part, int64_t part_cs, int64_t part_ss, int n_part,
                                 const float* theta, int64_t theta_cs, float inv_N,
                                 float* out, int64_t out_cs, int64_t n) {
+    dgprf_pdl_sync();
     const int chain = blockIdx.y;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float g = 0.f;
@@ -99,7 +102,7 @@ int dgprf_launch_grad_finalize(const float* part, int64_t part_cs, int64_t part_
     if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
     { ProfScope _ps("k_grad_finalize", st);
-      k_grad_finalize<<<dim3(blocks, n_chains), 256, 0, st>>>(part, part_cs, part_ss, n_part, theta, theta_cs, inv_N, out, out_cs, n); }
+      DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_grad_finalize, dim3(blocks, n_chains), dim3(256), 0, st, part, part_cs, part_ss, n_part, theta, theta_cs, inv_N, out, out_cs, n)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
@@ -118,6 +121,7 @@ __device__ __forceinline__ float slab_sum_rt(const SlabMat& m, int chain, int64_
     return v;
 }
 __global__ void __launch_bounds__(256) k_hyper_partial(const HypArgs a) {
+    dgprf_pdl_sync();
     __shared__ float red_a[8][33];
     __shared__ float red_b[8][33];
     __shared__ float red[32];
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(256) k_hyper_partial(const HypArgs a) {
     if (threadIdx.x == 0) part[2 * a.d] = acc;
 }
 __global__ void __launch_bounds__(256) k_hyper_final(const HypArgs a) {
+    dgprf_pdl_sync();
     const int chain = blockIdx.x;
     const float* part = a.part + chain * a.part_cs;
     float* gH = a.gH + chain * a.gh_cs;
@@ -185,8 +190,8 @@ int dgprf_launch_hyper_reduce(const HypArgs& a0, int n_chains, cudaStream_t st) 
     a.n_rb = ceil_div(a.B, a.rows_per);
     {
         ProfScope _ps("k8_hyper_reduce", st);
-        k_hyper_partial<<<dim3(a.n_rb, n_chains), 256, 0, st>>>(a);
-        k_hyper_final<<<n_chains, 256, 0, st>>>(a);
+        DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_hyper_partial, dim3(a.n_rb, n_chains), dim3(256), 0, st, a));
+        DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_hyper_final, dim3(n_chains), dim3(256), 0, st, a));
     }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;

@@ -9,6 +9,7 @@
 #include "tc_common.cuh"
 
 __global__ void __launch_bounds__(256) k_prep_layers(const __grid_constant__ PrepArgs a) {
+    dgprf_pdl_sync();
     __shared__ float tile[32][33];
     const PrepLayer& y = a.L[blockIdx.y];
     const int chain = blockIdx.z;
@@ -90,7 +91,7 @@ int dgprf_launch_prep_layers(const PrepArgs& a, int n_chains, cudaStream_t st) {
         if (t > max_tasks) max_tasks = t;
     }
     if (max_tasks == 0) return DGPRF_OK;
-    { ProfScope _ps("k_prep_layers", st); k_prep_layers<<<dim3(max_tasks, a.n_layers, n_chains), 256, 0, st>>>(a); }
+    { ProfScope _ps("k_prep_layers", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k_prep_layers, dim3(max_tasks, a.n_layers, n_chains), dim3(256), 0, st, a)); }
     DGPRF_CHECK_CUDA(cudaGetLastError());
     return DGPRF_OK;
 }
