@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(256) k_hyper_final(const HypArgs a) {
     }
 }
 
-// row blocks of the hyper reduction for a minibatch of B rows: <= 2 per SM, >= 128 rows each
+// row blocks of the hyper reduction for a minibatch of B rows: <= 2 per SM, >= 16 rows each.  (128 rows per block left a
+// 1000-row minibatch on 8 CTAs whose threads walked 16 rows x 8 slabs one dependent round trip after the other: 30-47 us
+// per layer, 60 % of a full-Bayesian step at the configs[1] shape.)
 int dgprf_hyper_row_blocks(int B) {
-    int n = ceil_div(B, 128);
+    int n = ceil_div(B, 16);
     return n < 1 ? 1 : (n > 296 ? 296 : n);
 }
 
