@@ -546,6 +546,53 @@ extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* 
     return DGPRF_OK;
 }
 
+extern "C" int dgprf_gradients(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B, int mode,
+                               void* ws, size_t ws_bytes, float* gW, int64_t gw_cs, float* gH, int64_t gh_cs,
+                               float prior_inv_N, int prior_hyper, float* ll_sum, float inv_B, int allow_fused, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "gradients need a TRAIN/HYPER workspace");
+    DGPRF_REQUIRE(X && Y, "X/Y is NULL");
+    DGPRF_REQUIRE(gH == nullptr || mode == DGPRF_MODE_HYPER, "hyper gradients need a HYPER workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float invB_default = 1.f / (float)B;
+    if (inv_B <= 0.f) inv_B = invB_default;
+    int n_part = w.RS;
+    if (allow_fused && mode == DGPRF_MODE_TRAIN && w.RSF > 0 && inv_B == invB_default) {
+        bool fused = false;                              // (no update requested: the kernel stops after the gradient slabs)
+        rc = (w.K10 ? dgprf_launch_step_cluster : dgprf_launch_step_rows)(
+            m, X, x_cs, Y, y_cs, B, wsf(ws, w.gwpart), w.n_gwpart, w.w_len, wsf(ws, w.llpart), w.n_llpart, nullptr, nullptr, 0,
+            reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.gridbar), nullptr, &fused, st);
+        if (rc) return rc;
+        if (ll_sum) {
+            rc = dgprf_launch_sum_rows(wsf(ws, w.llpart), w.n_llpart, w.RSF, ll_sum, m->n_chains, st);
+            if (rc) return rc;
+        }
+        n_part = w.RSF;
+    } else {
+        rc = forward_impl(m, w, X, x_cs, B, mode, ws, nullptr, st);
+        if (rc) return rc;
+        rc = loglik_impl(m, w, Y, y_cs, B, mode, ws, nullptr, nullptr, ll_sum, inv_B, st);
+        if (rc) return rc;
+        rc = backward_impl(m, w, X, x_cs, B, mode, ws, st);
+        if (rc) return rc;
+    }
+    if (gW) {
+        DGPRF_REQUIRE(gw_cs >= w.w_len, "gW chain stride %lld < %lld", (long long)gw_cs, (long long)w.w_len);
+        rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), w.n_gwpart, w.w_len, n_part, m->w_base, m->w_cs, prior_inv_N, gW, gw_cs,
+                                        w.w_len, m->n_chains, st);
+        if (rc) return rc;
+    }
+    if (gH) {
+        DGPRF_REQUIRE(gh_cs >= w.h_len, "gH chain stride %lld < %lld", (long long)gh_cs, (long long)w.h_len);
+        rc = dgprf_launch_grad_finalize(wsf(ws, w.ghyp), w.h_len, 0, 1, m->h_base, m->h_cs, prior_hyper ? prior_inv_N : 0.f, gH, gh_cs,
+                                        w.h_len, m->n_chains, st);
+        if (rc) return rc;
+    }
+    return DGPRF_OK;
+}
+
 // ---- update -----------------------------------------------------------------------------------------
 // the device-resident step base of dgprf_sgmcmc_step_graph, attached to every UpdArgs built during that call
 static thread_local const unsigned long long* g_step_dev = nullptr;

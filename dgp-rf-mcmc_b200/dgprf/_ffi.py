@@ -60,6 +60,7 @@ SIGNATURES = {
     "dgprf_loglik": (_I, [_MP, _VP, _I64, _I, _I, _VP, _SZ, _VP, _VP, _VP, _F, _VP]),
     "dgprf_backward": (_I, [_MP, _VP, _I64, _I, _I, _VP, _SZ, _VP]),
     "dgprf_grad_finalize": (_I, [_MP, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP]),
+    "dgprf_gradients": (_I, [_MP, _VP, _I64, _VP, _I64, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP, _F, _I, _VP]),
     "dgprf_sgmcmc_update": (_I, [_VP, _VP, _I64, _I64, _I, _VP, _I64, _I, _I64, _SP, _I,
                                  _F, _F, _F, _F, _I, _U64, _U64, _VP, _VP, _VP]),
     "dgprf_sgmcmc_step": (_I, [_MP, _VP, _I64, _VP, _I64, _I, _I,

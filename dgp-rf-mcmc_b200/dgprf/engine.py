@@ -293,9 +293,11 @@ class Engine:
         return ll, aux, tot
 
     def gradients(self, X, Y, data_size: float, hyper: bool, prior_w: bool, prior_h: bool,
-                  m: Optional[_ffi.Model] = None, inv_B: Optional[float] = None, out_flat: Optional[torch.Tensor] = None):
+                  m: Optional[_ffi.Model] = None, inv_B: Optional[float] = None, out_flat: Optional[torch.Tensor] = None,
+                  fused: bool = True):
         """Forward + likelihood seed + backward; returns (ll_sum [C], gW [C,w_len], gH [C,h_len]|None).
-        gW/gH are dU/dtheta of models/dgp.py:161-182 (prior terms theta/N added on request)."""
+        gW/gH are dU/dtheta of models/dgp.py:161-182 (prior terms theta/N added on request).  ONE C call (dgprf_gradients):
+        W-only gradients of a model the row-fused step kernel takes run in one launch (fused=False keeps the layered kernels)."""
         assert prior_w or not prior_h, "hyper prior without W prior is not a mode of the reference"
         m = self.model() if m is None else m
         X, x_cs, Y, y_cs, B = self._xy(X, Y, m.n_chains)
@@ -314,15 +316,11 @@ class Engine:
             tot = torch.empty(Cn, device=self.device, dtype=torch.float32)
             gW = torch.empty(Cn, self.layout.w_len, device=self.device, dtype=torch.float32)
         gH = torch.empty(Cn, self.layout.h_len, device=self.device, dtype=torch.float32) if hyper else None
-        a = (C.byref(m),)
-        _ffi.check(L.dgprf_forward(*a, X.data_ptr(), x_cs, B, mode, ws.data_ptr(), ws.numel(), None, st))
-        _ffi.check(L.dgprf_loglik(*a, Y.data_ptr(), y_cs, B, mode, ws.data_ptr(), ws.numel(), None, None,
-                                  tot.data_ptr(), (1.0 / B) if inv_B is None else float(inv_B), st))
-        _ffi.check(L.dgprf_backward(*a, X.data_ptr(), x_cs, B, mode, ws.data_ptr(), ws.numel(), st))
         inv_N = 1.0 / float(data_size)
-        _ffi.check(L.dgprf_grad_finalize(*a, B, mode, ws.data_ptr(), ws.numel(), gW.data_ptr(), gW.shape[1],
-                                         gH.data_ptr() if hyper else None, self.layout.h_len,
-                                         inv_N if (prior_w or prior_h) else 0.0, int(prior_h), st))
+        _ffi.check(L.dgprf_gradients(C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, mode, ws.data_ptr(), ws.numel(),
+                                     gW.data_ptr(), gW.shape[1], gH.data_ptr() if hyper else None, self.layout.h_len,
+                                     inv_N if (prior_w or prior_h) else 0.0, int(prior_h), tot.data_ptr(),
+                                     0.0 if inv_B is None else float(inv_B), int(bool(fused)), st))
         return tot, gW, gH
 
     def step(self, X, Y, data_size: float, lr: float, momentum_decay: float, temperature: float,

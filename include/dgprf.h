@@ -140,6 +140,16 @@ int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* ws, size_t 
                         float* gW, int64_t gw_cs, float* gH, int64_t gh_cs,
                         float prior_inv_N, int prior_hyper, void* stream);
 
+/* The whole gradient pass behind tf.GradientTape in one call (models/dgp.py:186-204 of sgmcmc_update, :246-251 of
+ * precond_update, experiments/utils_training.py:341-354 of the M-step):
+ *   dgprf_forward(mode) + dgprf_loglik(inv_B) + dgprf_backward + dgprf_grad_finalize.
+ * With allow_fused != 0, mode == DGPRF_MODE_TRAIN and inv_B == 1/B (pass inv_B <= 0 for that default) a model the row-fused
+ * step kernel takes runs forward, likelihood seed and backward in ONE launch (the kernel of dgprf_sgmcmc_step without its
+ * update); every other case runs the layered sequence.  ll_sum [C] (nullable) receives sum_i log p(y_i | f_i). */
+int dgprf_gradients(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B, int mode,
+                    void* ws, size_t ws_bytes, float* gW, int64_t gw_cs, float* gH, int64_t gh_cs,
+                    float prior_inv_N, int prior_hyper, float* ll_sum, float inv_B, int allow_fused, void* stream);
+
 /* The update loop of sgmcmc_update (models/dgp.py:206-216) over a flat parameter buffer:
  *   h = sqrt(lr/N); [m <- N(0,1)]; m <- beta m - h N g + sqrt(2 (1-beta) T M) eps;
  *   theta <- theta + (h/M) m

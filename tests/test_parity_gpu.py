@@ -67,6 +67,30 @@ def test_gradients(name, full_bayes):
         assert rel_err(g[n], ref) < RTOL, n
 
 
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_w_gradients_fused_and_layered_kernels(name):
+    """dgprf_gradients runs the row-fused step kernel (without its update) where the model is eligible and the layered
+    forward / seed / backward kernels otherwise or on request: both against the oracle, and the routing itself."""
+    from dgprf import _ffi
+    model, X, Y, c = make_model(name)
+    p = oracle_params(model)
+    u_ref, g_ref = O.grads_autograd(p, X.double(), Y.double(), c["N"], False)
+    e = model._engine
+    ll_ref = float(O.log_likelihood(p, X.double(), Y.double()).sum())
+    for fused in (True, False):
+        _ffi.profile_start()
+        tot, gW, _ = e.gradients(X, Y, c["N"], hyper=False, prior_w=True, prior_h=False, fused=fused)
+        kernels = [nm for nm, _ in _ffi.profile_stop()]
+        if fused and max(c["n_gp"]) <= 32:                          # every small config with n_gp <= 32 is K10's
+            assert kernels[0] == "k10_step_cluster", kernels
+        if not fused:
+            assert not any(k.startswith(("k10_", "k9_")) for k in kernels), kernels
+        assert float(tot[0]) == pytest.approx(ll_ref, rel=RTOL)
+        g = e.named_from_flat(gW, "w")
+        for n, ref in g_ref.items():
+            assert rel_err(g[n].reshape(ref.shape), ref) < RTOL, (n, fused)
+
+
 @pytest.mark.parametrize("name", ["protein_small", "mnist_small", "ragged_mixed"])
 def test_em_hyper_gradients(name):
     """M-step gradients: W detached, prior term zero (experiments/utils_training.py:345-354)."""
