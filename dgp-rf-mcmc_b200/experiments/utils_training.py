@@ -213,16 +213,17 @@ def _count_batches(ds):
 
 def _run_sampler(model, ds_train, ds_test, train_size, lr_0, momentum_decay, full_bayesian, precond_type, K_batches,
                  second_moment_centered, resample_in_cycle_head, total_epochs, start_sampling_epoch, epochs_per_cycle,
-                 print_epoch_cycle, Y_std, task, collect_W, verbose, graph=False, on_sample=None):
+                 print_epoch_cycle, Y_std, task, collect_W, verbose, graph=None, on_sample=None):
     """The loop of utils_training.py:41-77 / :121-152 / :206-236.  graph=True replays one captured CUDA graph per epoch
-    (needs a DeviceDataset and the identity preconditioner: masses are baked into the graph)."""
+    (needs a DeviceDataset and the identity preconditioner: masses are baked into the graph); graph=None (the default) does so
+    whenever that is possible and issues the steps one by one otherwise; graph=False never captures.  Bit-identical either way."""
     if precond_type != 'identity' and K_batches is None and second_moment_centered is None:
         raise ValueError("Args K_batches or second_moment_centered shouldn't be None!")
     iterations_per_epoch = _count_batches(ds_train)
     cycle_length = epochs_per_cycle * iterations_per_epoch
     log_p, aux, W_samples = [], [], []
     log_Y_std = math.log(Y_std)
-    use_graph = bool(graph)
+    use_graph = graph is None or bool(graph)            # None: one graph launch per epoch whenever the set-up allows it
     if use_graph:
         why = None
         if precond_type != 'identity':
@@ -234,7 +235,10 @@ def _run_sampler(model, ds_train, ds_test, train_size, lr_0, momentum_decay, ful
         elif not (ds_train.drop_remainder or ds_train.N % ds_train.batch_size == 0):
             why = "all minibatches of an epoch must have the same size (drop_remainder=True)"
         if why is not None:
-            raise ValueError(f"graph=True is not possible here: {why}")
+            if graph is None:
+                use_graph = False                           # default: fall back to one launch sequence per step
+            else:
+                raise ValueError(f"graph=True is not possible here: {why}")
     graphs = {}
 
     def evaluate(ds):
@@ -343,7 +347,7 @@ def regression_train(model, dataset_name='boston', batch_size=200, data_dir='./d
                      precond_type='identity', K_batches=None, second_moment_centered=None,
                      resample_in_cycle_head=False,
                      total_epochs=5000, start_sampling_epoch=2000, epochs_per_cycle=50,
-                     print_epoch_cycle=100, *, data=None, verbose=True, graph=False):
+                     print_epoch_cycle=100, *, data=None, verbose=True, graph=None):
     """Cyclical SG-MCMC for regression (utils_training.py:11-91, same positional signature): burn-in at T=0 and lr_0,
     then lr = lr_0 rate^2 with a cosine cycle, one posterior sample at every cycle end; returns
     (log_p [S, N_test], mse [S, N_test]).  Extensions (keyword-only): `data=(ds_train, ds_test, train_size, Y_std)`
@@ -360,7 +364,7 @@ def classification_train(model, dataset_name='mnist', batch_size=200, data_dir='
                          precond_type='identity', K_batches=None, second_moment_centered=None,
                          resample_in_cycle_head=False,
                          total_epochs=5000, start_sampling_epoch=2000, epochs_per_cycle=50,
-                         print_epoch_cycle=100, *, data=None, verbose=True, graph=False):
+                         print_epoch_cycle=100, *, data=None, verbose=True, graph=None):
     """utils_training.py:93-172; returns (log_p [S, N_test], acc [S])."""
     ds_train, ds_test, train_size, _ = _resolve(data, dataset_name, batch_size, data_dir, "cls", verbose)
     _, log_p, acc = _run_sampler(model, ds_train, ds_test, train_size, lr_0, momentum_decay, full_bayesian, precond_type,
@@ -371,7 +375,7 @@ def classification_train(model, dataset_name='mnist', batch_size=200, data_dir='
 
 def MCEM_sampler(model, ds_train, ds_test, train_size, Y_std=1.0, task="reg", lr_0=0.01, momentum_decay=0.9,
                  precond_type='identity', K_batches=None, second_moment_centered=None, resample_in_cycle_head=True,
-                 start_sampling_epoch=2000, epochs_per_cycle=50, verbose=False, graph=False):
+                 start_sampling_epoch=2000, epochs_per_cycle=50, verbose=False, graph=None):
     """E-step sampler factory (utils_training.py:174-337): sampler(num_samples) runs burn-in + num_samples cycles
     with the hyper-parameters fixed (full_bayesian=False) and returns (W_samples, log_p, mse | acc)."""
     def sampler(num_samples=100, print_epoch_cycle=100):
@@ -385,7 +389,7 @@ def MCEM_sampler(model, ds_train, ds_test, train_size, Y_std=1.0, task="reg", lr
 def MCEM_sampler_UCI(model, dataset_name='boston', batch_size=200, data_dir='./data/',
                      lr_0=0.01, momentum_decay=0.9,
                      precond_type='identity', K_batches=None, second_moment_centered=None,
-                     resample_in_cycle_head=True, start_sampling_epoch=2000, epochs_per_cycle=50, *, data=None, graph=False):
+                     resample_in_cycle_head=True, start_sampling_epoch=2000, epochs_per_cycle=50, *, data=None, graph=None):
     """utils_training.py:174-256 (same signature): the E-step sampler over a UCI regression set."""
     ds_train, ds_test, train_size, Y_std = _resolve(data, dataset_name, batch_size, data_dir, "reg")
     return MCEM_sampler(model, ds_train, ds_test, train_size, Y_std, "reg", lr_0, momentum_decay, precond_type, K_batches,
@@ -396,7 +400,7 @@ def MCEM_sampler_classification(model, dataset_name='mnist', batch_size=200, dat
                                 lr_0=0.01, momentum_decay=0.9,
                                 precond_type='identity', K_batches=None, second_moment_centered=None,
                                 resample_in_cycle_head=True, start_sampling_epoch=2000, epochs_per_cycle=50, *, data=None,
-                                graph=False):
+                                graph=None):
     """utils_training.py:258-337 (same signature): the E-step sampler over a tfds-style classification set."""
     ds_train, ds_test, train_size, _ = _resolve(data, dataset_name, batch_size, data_dir, "cls")
     return MCEM_sampler(model, ds_train, ds_test, train_size, 1.0, "cls", lr_0, momentum_decay, precond_type, K_batches,

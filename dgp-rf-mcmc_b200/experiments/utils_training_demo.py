@@ -41,7 +41,7 @@ def regression_train_demo(model_demo, ds_train, ds_test, train_size, batch_size,
                           lr_0=0.01, momentum_decay=0.9,
                           resample_in_cycle_head=True,
                           total_epochs=5000, start_sampling_epoch=2000, epochs_per_cycle=50,
-                          print_epoch_cycle=100, *, verbose=True, graph=False):
+                          print_epoch_cycle=100, *, verbose=True, graph=None):
     """W-only cyclical SGHMC with the identity preconditioner; returns (log_p [S, N], mse [S, N], lines, W):
     lines[s][l] = output of GP layer l at X_test for sample s, W['W_l'][s] = ndarray [F_l, g_l]."""
     _check_sizes(train_size, batch_size)
@@ -54,7 +54,7 @@ def regression_train_demo(model_demo, ds_train, ds_test, train_size, batch_size,
 
 def MCEM_sampler_demo(model_demo, ds_train, ds_test, train_size, batch_size, X_test,
                       lr_0=0.01, momentum_decay=0.9, resample_in_cycle_head=False,
-                      start_sampling_epoch=0, epochs_per_cycle=50, *, verbose=True, graph=False):
+                      start_sampling_epoch=0, epochs_per_cycle=50, *, verbose=True, graph=None):
     def sampler(num_samples=100, return_lines_Wdict=False, print_epoch_cycle=100):
         _check_sizes(train_size, batch_size)
         col = _Collector(model_demo, X_test) if return_lines_Wdict else None

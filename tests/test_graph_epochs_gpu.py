@@ -55,6 +55,40 @@ def test_graph_epoch_equals_the_same_steps_issued_one_by_one():
     assert torch.isfinite(a._engine.theta_w).all()
 
 
+@pytest.mark.parametrize("variant", ["tf32", "full_bayes"])
+def test_graph_epoch_of_the_layered_paths(variant):
+    """The layered kernels (tensor-core mode; full-Bayesian step) launch with programmatic stream serialization: a captured
+    epoch of them must replay to exactly what the same steps give one by one."""
+    X, Y, _, _ = _toy(3, N=512, D=9)
+    fb = variant == "full_bayes"
+
+    def make():
+        torch.manual_seed(4)
+        m = RegressionDGP(9, 1, n_hidden_layers=2, n_rf=256, n_gp=[9, 1], input_cat=True)
+        m.seed(4)
+        if variant == "tf32":
+            m.set_precision("tf32")
+        m.precond_update(None, 512, precond_type="identity", full_bayesian=fb)
+        return m
+    a, b = make(), make()
+    b._engine.mom_w.copy_(a._engine.mom_w)
+    b._engine.mom_h.copy_(a._engine.mom_h)
+    dsa = DeviceDataset(X, Y, 256, seed=7); dsb = DeviceDataset(X, Y, 256, seed=7)
+    lrs = [0.004, 0.003]
+    dsb.reshuffle()
+    g = EpochGraph(b, dsb, 512, lrs, 0.9, 1.0, False, fb)
+    for epoch in range(3):
+        for i, (xb, yb) in enumerate(dsa):
+            a.sgmcmc_update(xb, yb, 512, lr=lrs[i], momentum_decay=0.9, temperature=1.0, full_bayesian=fb)
+        if epoch > 0:
+            dsb.reshuffle()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(a._engine.theta_w, b._engine.theta_w) and torch.equal(a._engine.mom_w, b._engine.mom_w)
+    assert torch.equal(a._engine.theta_h, b._engine.theta_h)
+    assert torch.isfinite(a._engine.theta_w).all()
+
+
 @pytest.mark.parametrize("resample", [False, True])
 def test_driver_with_graph_epochs_is_bit_identical_to_the_eager_driver(resample):
     X, Y, Xt, Yt = _toy(2)
