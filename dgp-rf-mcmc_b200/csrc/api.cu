@@ -447,6 +447,18 @@ extern "C" int dgprf_loglik(const dgprf_model* m, const float* Y, int64_t y_cs, 
 }
 
 // ---- backward -------------------------------------------------------------------------------------
+// Per-layer hook of the layered reverse pass (thread-local): called on the host right after the kernels of layer l have been
+// enqueued, top layer first.  The data-parallel step uses it to start the all-reduce of a layer's gradient slice on a side
+// stream while the layers below are still running (dgprf/dist.py: data_parallel_step).
+static thread_local dgprf_layer_hook g_bwd_hook = nullptr;
+static thread_local void* g_bwd_hook_user = nullptr;
+
+extern "C" int dgprf_set_backward_hook(dgprf_layer_hook hook, void* user) {
+    g_bwd_hook = hook;
+    g_bwd_hook_user = hook ? user : nullptr;
+    return DGPRF_OK;
+}
+
 static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X, int64_t x_cs, int B, int mode,
                          void* ws, cudaStream_t st) {
     const int hyper = mode == DGPRF_MODE_HYPER;
@@ -508,6 +520,7 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
             rc = dgprf_launch_hyper_reduce(h, m->n_chains, st);
             if (rc) return rc;
         }
+        if (g_bwd_hook) g_bwd_hook(l, g_bwd_hook_user);
     }
     return DGPRF_OK;
 }
@@ -544,6 +557,26 @@ extern "C" int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* 
         if (rc) return rc;
     }
     return DGPRF_OK;
+}
+
+extern "C" int dgprf_grad_finalize_layer(const dgprf_model* m, int layer, int B, int mode, void* ws, size_t ws_bytes,
+                                         float* gW, int64_t gw_cs, float prior_inv_N, void* stream) {
+    WsLayout w;
+    int rc = check_ws(m, B, mode, ws, ws_bytes, &w);
+    if (rc) return rc;
+    DGPRF_REQUIRE(mode >= DGPRF_MODE_TRAIN, "grad_finalize_layer needs a TRAIN/HYPER workspace");
+    DGPRF_REQUIRE(layer >= 0 && layer < m->n_layers, "layer %d out of range [0, %d)", layer, m->n_layers);
+    DGPRF_REQUIRE(gW != nullptr, "gW is NULL");
+    DGPRF_REQUIRE(gw_cs >= w.w_len, "gW chain stride %lld < %lld", (long long)gw_cs, (long long)w.w_len);
+    const dgprf_layer& y = m->layer[layer];
+    // the slice runs to the next tensor's offset (tensors are padded to 128-bit lanes; the whole-buffer finalize covers the
+    // padding too, and the update kernel walks whole lanes)
+    int64_t n = w.w_len - y.off_W;
+    for (int l = 0; l < m->n_layers; ++l)
+        if (m->layer[l].off_W > y.off_W && m->layer[l].off_W - y.off_W < n) n = m->layer[l].off_W - y.off_W;
+    DGPRF_REQUIRE(n >= (int64_t)layer_F(y) * y.g, "layer %d: W slice overlaps the next tensor", layer);
+    return dgprf_launch_grad_finalize(wsf(ws, w.gwpart) + y.off_W, w.n_gwpart, w.w_len, w.RS, m->w_base + y.off_W, m->w_cs,
+                                      prior_inv_N, gW + y.off_W, gw_cs, n, m->n_chains, (cudaStream_t)stream);
 }
 
 extern "C" int dgprf_gradients(const dgprf_model* m, const float* X, int64_t x_cs, const float* Y, int64_t y_cs, int B, int mode,

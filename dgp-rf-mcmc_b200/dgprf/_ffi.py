@@ -23,6 +23,7 @@ PREC_FP32, PREC_TF32 = 0, 1
 MODE_EVAL, MODE_TRAIN, MODE_HYPER = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)
+LAYER_HOOK = C.CFUNCTYPE(None, C.c_int, C.c_void_p)          # dgprf_layer_hook
 
 
 class Layer(C.Structure):
@@ -60,6 +61,8 @@ SIGNATURES = {
     "dgprf_loglik": (_I, [_MP, _VP, _I64, _I, _I, _VP, _SZ, _VP, _VP, _VP, _F, _VP]),
     "dgprf_backward": (_I, [_MP, _VP, _I64, _I, _I, _VP, _SZ, _VP]),
     "dgprf_grad_finalize": (_I, [_MP, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP]),
+    "dgprf_grad_finalize_layer": (_I, [_MP, _I, _I, _I, _VP, _SZ, _VP, _I64, _F, _VP]),
+    "dgprf_set_backward_hook": (_I, [_VP, _VP]),
     "dgprf_gradients": (_I, [_MP, _VP, _I64, _VP, _I64, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP, _F, _I, _VP]),
     "dgprf_sgmcmc_update": (_I, [_VP, _VP, _I64, _I64, _I, _VP, _I64, _I, _I64, _SP, _I,
                                  _F, _F, _F, _F, _I, _U64, _U64, _VP, _VP, _VP]),

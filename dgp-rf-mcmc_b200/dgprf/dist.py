@@ -15,10 +15,14 @@ Three sharding patterns of SURVEY section 8(e); only the third has a data-path c
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+_DP_OVERLAP_DEFAULT = os.environ.get("DGPRF_DP_OVERLAP", "1") != "0"
 
 
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
@@ -78,28 +82,81 @@ def combine_predictive(lse_local: torch.Tensor, n_samples_local: int, aux_sum_lo
     return float(lp), aux
 
 
+class _OverlapState:
+    """Side stream, per-layer events and bucket boundaries of the overlapped data-parallel step (one per engine)."""
+
+    def __init__(self, engine, min_bucket_floats: int):
+        lay = engine.layout
+        self.comm = torch.cuda.Stream(device=engine.device)
+        self.events = [torch.cuda.Event() for _ in lay.off_W]
+        # buckets are contiguous runs of the flat buffer, built from the top layer down (the order the reverse pass retires
+        # them): a layer closes a bucket once the run holds min_bucket_floats, layer 0 closes the last one
+        self.flush_at = set()
+        hi = lay.w_len + 1
+        for l in range(len(lay.off_W) - 1, -1, -1):
+            if l == 0 or hi - lay.off_W[l] >= min_bucket_floats:
+                self.flush_at.add(l)
+                hi = lay.off_W[l]
+
+
 def data_parallel_step(engine, X_local: torch.Tensor, Y_local: torch.Tensor, global_rows: int, data_size: float,
                        lr: float, momentum_decay: float, temperature: float = 1.0, resample: bool = False,
-                       seed: int = 0, step: int = 0, group=None) -> torch.Tensor:
+                       seed: int = 0, step: int = 0, group=None, overlap: Optional[bool] = None,
+                       min_bucket_floats: int = 65536) -> torch.Tensor:
     """One W-only sgmcmc_update (models/dgp.py:184-216) of a minibatch whose rows are split over the ranks.
 
     Every rank runs forward / likelihood seed / backward on its rows (CUDA kernels, data term only) with the seed scaled
-    by 1 / B_global, so its flat gradient is already its share of the global one; ONE all-reduce(sum) of
-    [gW | sum_i ll_i] (written in place by the kernels, no staging copy), and every rank applies the update
-    kernel to its replica with the same Philox (seed, step): the prior term theta/N is added inside the update,
-    once, after the reduction; replicas stay bit-identical without a broadcast.  Returns sum_i ll_i [C]."""
+    by 1 / B_global, so its flat gradient is already its share of the global one; the flat buffer [gW | sum_i ll_i]
+    (written in place by the kernels, no staging copy) is all-reduced (sum), and every rank applies the update kernel to
+    its replica with the same Philox (seed, step): the prior term theta/N is added inside the update, once, after the
+    reduction; replicas stay bit-identical without a broadcast.  Returns sum_i ll_i [C].
+
+    overlap (default: on when world > 1; DGPRF_DP_OVERLAP=0 turns it off): the reverse pass retires the layers top-down, and
+    a layer's gradient slice is final as soon as its backward kernel has run -- so the slab sum of that slice and its
+    all-reduce are issued on a side stream from a per-layer host hook (dgprf_set_backward_hook) and run UNDER the backward
+    kernels of the layers below; only the bucket of layer 0 is exposed.  Every element is still reduced exactly once, by
+    the same collective, so the replicas stay bit-identical; overlap=False is one all-reduce of the whole buffer."""
     from . import _ffi
     w_len = engine.layout.w_len
     assert engine.C == 1, "the data-parallel step drives one replica per rank"
     flat = getattr(engine, "_dp_flat", None)
     if flat is None:
-        flat = engine._dp_flat = torch.empty(w_len + 1, device=engine.device, dtype=torch.float32)
-    # forward / seed / backward of the local rows with the seed already scaled by 1 / B_global: the flat buffer
-    # [gW | sum_i ll_i] is written in place by the kernels and is the all-reduce payload as it stands
-    engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False, inv_B=1.0 / float(global_rows),
-                     out_flat=flat)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat = engine._dp_flat = torch.zeros(w_len + 1, device=engine.device, dtype=torch.float32)
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if overlap is None:
+        overlap = world > 1 and _DP_OVERLAP_DEFAULT
+    if overlap:
+        key = ("_dp_overlap", int(min_bucket_floats))
+        st = getattr(engine, "_dp_overlap_state", None)
+        if st is None or st[0] != key:
+            st = engine._dp_overlap_state = (key, _OverlapState(engine, int(min_bucket_floats)))
+        st = st[1]
+        main = torch.cuda.current_stream()
+        off_W = engine.layout.off_W
+        hi = [w_len + 1]
+
+        def hook(l, finalize_layer):
+            ev = st.events[l]
+            ev.record(main)
+            st.comm.wait_event(ev)
+            finalize_layer(l, st.comm.cuda_stream)
+            if l in st.flush_at:
+                if world > 1:
+                    with torch.cuda.stream(st.comm):
+                        dist.all_reduce(flat[off_W[l]:hi[0]], op=dist.ReduceOp.SUM, group=group)
+                hi[0] = off_W[l]
+
+        engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False,
+                         inv_B=1.0 / float(global_rows), out_flat=flat, layer_hook=hook)
+        assert hi[0] == 0, "a layer of the reverse pass did not report"
+        main.wait_stream(st.comm)
+    else:
+        # forward / seed / backward of the local rows with the seed already scaled by 1 / B_global: the flat buffer
+        # [gW | sum_i ll_i] is written in place by the kernels and is the all-reduce payload as it stands
+        engine.gradients(X_local, Y_local, data_size, hyper=False, prior_w=False, prior_h=False,
+                         inv_B=1.0 / float(global_rows), out_flat=flat)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     sw, nsw, _, _ = engine._segments()
     _ffi.check(_ffi.lib().dgprf_sgmcmc_update(
         engine.theta_w.data_ptr(), engine.mom_w.data_ptr(), w_len, w_len, 1, flat.data_ptr(), w_len, 1, 0,

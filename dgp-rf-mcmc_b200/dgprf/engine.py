@@ -294,8 +294,11 @@ class Engine:
 
     def gradients(self, X, Y, data_size: float, hyper: bool, prior_w: bool, prior_h: bool,
                   m: Optional[_ffi.Model] = None, inv_B: Optional[float] = None, out_flat: Optional[torch.Tensor] = None,
-                  fused: bool = True):
+                  fused: bool = True, layer_hook=None):
         """Forward + likelihood seed + backward; returns (ll_sum [C], gW [C,w_len], gH [C,h_len]|None).
+        layer_hook(l, finalize_layer): called on the host as soon as the reverse pass of layer l is enqueued (top layer
+        first; layered kernels only); finalize_layer(l, cuda_stream) sums that layer's partial slabs into gW on the stream
+        given.  The hook owns the ordering against the current stream (dgprf/dist.py: data_parallel_step).
         gW/gH are dU/dtheta of models/dgp.py:161-182 (prior terms theta/N added on request).  ONE C call (dgprf_gradients):
         W-only gradients of a model the row-fused step kernel takes run in one launch (fused=False keeps the layered kernels)."""
         assert prior_w or not prior_h, "hyper prior without W prior is not a mode of the reference"
@@ -317,10 +320,38 @@ class Engine:
             gW = torch.empty(Cn, self.layout.w_len, device=self.device, dtype=torch.float32)
         gH = torch.empty(Cn, self.layout.h_len, device=self.device, dtype=torch.float32) if hyper else None
         inv_N = 1.0 / float(data_size)
-        _ffi.check(L.dgprf_gradients(C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, mode, ws.data_ptr(), ws.numel(),
-                                     gW.data_ptr(), gW.shape[1], gH.data_ptr() if hyper else None, self.layout.h_len,
-                                     inv_N if (prior_w or prior_h) else 0.0, int(prior_h), tot.data_ptr(),
-                                     0.0 if inv_B is None else float(inv_B), int(bool(fused)), st))
+        if layer_hook is None:
+            _ffi.check(L.dgprf_gradients(C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, mode, ws.data_ptr(), ws.numel(),
+                                         gW.data_ptr(), gW.shape[1], gH.data_ptr() if hyper else None, self.layout.h_len,
+                                         inv_N if (prior_w or prior_h) else 0.0, int(prior_h), tot.data_ptr(),
+                                         0.0 if inv_B is None else float(inv_B), int(bool(fused)), st))
+            return tot, gW, gH
+        # layered reverse pass with a per-layer host hook (data-parallel step): the caller finalizes gW slice by slice
+        # (finalize_layer below) as the layers retire, so no whole-buffer finalize here (gW = NULL)
+        assert not hyper, "the per-layer hook drives W-only gradients"
+        prior = inv_N if prior_w else 0.0
+        gw_ptr, gw_cs, ws_ptr, ws_n = gW.data_ptr(), gW.shape[1], ws.data_ptr(), ws.numel()
+        failure = []
+
+        def finalize_layer(l, stream_ptr):
+            _ffi.check(L.dgprf_grad_finalize_layer(C.byref(m), l, B, mode, ws_ptr, ws_n, gw_ptr, gw_cs, prior, stream_ptr))
+
+        def _hook(l, _user):
+            try:
+                layer_hook(l, finalize_layer)
+            except BaseException as exc:        # a ctypes callback cannot raise through the C frames
+                failure.append(exc)
+
+        cb = _ffi.LAYER_HOOK(_hook)
+        L.dgprf_set_backward_hook(C.cast(cb, C.c_void_p), None)
+        try:
+            _ffi.check(L.dgprf_gradients(C.byref(m), X.data_ptr(), x_cs, Y.data_ptr(), y_cs, B, mode, ws_ptr, ws_n,
+                                         None, gw_cs, None, self.layout.h_len, 0.0, 0, tot.data_ptr(),
+                                         0.0 if inv_B is None else float(inv_B), 0, st))
+        finally:
+            L.dgprf_set_backward_hook(None, None)
+        if failure:
+            raise failure[0]
         return tot, gW, gH
 
     def step(self, X, Y, data_size: float, lr: float, momentum_decay: float, temperature: float,

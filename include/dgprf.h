@@ -140,6 +140,19 @@ int dgprf_grad_finalize(const dgprf_model* m, int B, int mode, void* ws, size_t 
                         float* gW, int64_t gw_cs, float* gH, int64_t gh_cs,
                         float prior_inv_N, int prior_hyper, void* stream);
 
+/* dgprf_grad_finalize restricted to the W tensor of ONE layer (the slice [off_W, off_W + F*g) of gW): the data-parallel
+ * split of a large minibatch (the 1/B mean of models/dgp.py:174 taken over the GLOBAL minibatch)
+ * reduces a layer's slice across GPUs while the reverse pass of the layers below is still running. */
+int dgprf_grad_finalize_layer(const dgprf_model* m, int layer, int B, int mode, void* ws, size_t ws_bytes,
+                              float* gW, int64_t gw_cs, float prior_inv_N, void* stream);
+
+/* Host hook of the layered reverse pass (dgprf_backward, and dgprf_gradients with allow_fused == 0): called on the calling
+ * thread right after the kernels of layer `layer` have been enqueued, top layer first (the order tape.gradient walks the
+ * layers, models/dgp.py:194-204).  Thread-local; hook == NULL clears it.  Nothing is synchronised: the hook orders its own
+ * work against `stream` (event record + wait). */
+typedef void (*dgprf_layer_hook)(int layer, void* user);
+int dgprf_set_backward_hook(dgprf_layer_hook hook, void* user);
+
 /* The whole gradient pass behind tf.GradientTape in one call (models/dgp.py:186-204 of sgmcmc_update, :246-251 of
  * precond_update, experiments/utils_training.py:341-354 of the M-step):
  *   dgprf_forward(mode) + dgprf_loglik(inv_B) + dgprf_backward + dgprf_grad_finalize.
