@@ -128,7 +128,8 @@ struct WsLayout {
     int RSF;       // row groups of the row-fused step (0: not eligible) -- also gW slabs
     int K10;       // the row-fused step is the cluster-split tensor-pipe kernel (RSF = its row tiles), else K9
     int64_t w_len, h_len, n_dflast, n_gwpart, n_llpart;
-    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, fsum, total;
+    size_t dflast, gwpart, ghyp, llsum, likpart, llpart, gridbar, dfsum, hpart, fsum, sumctr, total;
+    int64_t n_sumctr;
     int64_t n_dfsum, n_hpart, n_fsum;
 };
 
@@ -259,10 +260,14 @@ static int make_layout(const dgprf_model* m, int B, int mode, WsLayout* w) {
     }
     for (int l = 0; l + 1 < m->n_layers; ++l)          // pre-summed dF of a pipelined TC backward (one slab instead of CS)
         if (w->L[l].bwd2 && (int64_t)B * m->layer[l].g > w->n_dfsum) w->n_dfsum = (int64_t)B * m->layer[l].g;
-    if (w->n_dfsum > 0) w->dfsum = take(w->n_dfsum);
+    if (w->n_dfsum > 0) w->dfsum = take(2 * w->n_dfsum);      // two buffers: layer l reads one while its kernel's tail fills the other
     for (int l = 1; l < m->n_layers; ++l)              // pre-summed F_{l-1} for a pipelined TC forward whose input comes in several slabs
         if (w->L[l].tc2 && w->L[l - 1].CSf > 1 && (int64_t)B * m->layer[l - 1].g > w->n_fsum) w->n_fsum = (int64_t)B * m->layer[l - 1].g;
-    if (w->n_fsum > 0) w->fsum = take(w->n_fsum);
+    if (w->n_fsum > 0) w->fsum = take(2 * w->n_fsum);
+    // tickets of the fused slab sums (pipelined kernels: the last column split of a row block adds the slabs): [fwd | bwd] x
+    // [chains][128-row blocks], zero between launches (the workspace is zero-initialised, a ticket resets itself)
+    w->n_sumctr = ceil_div(B, 128);
+    w->sumctr = take(2 * w->n_sumctr);
     w->total = off;
     return DGPRF_OK;
 }
@@ -348,6 +353,11 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
             if (rc) return rc;
         }
     }
+    // opt-in (DGPRF_FUSED_SLAB_SUMS=1), measured slower than the launches it removes: the ticket + sum are three to five DEPENDENT
+    // round trips at a CTA's tail (~1.8 us each under the other CTAs' streams), a PDL-overlapped k_sum_slabs launch is 7-17 us
+    // off the critical path of nothing (profiles/r02_fused_slab_sums.txt: configs[4] layer backward 523 -> 744 us, forward +8 us)
+    const bool fuse_sums = getenv("DGPRF_FUSED_SLAB_SUMS") != nullptr;
+    bool fsum_ready = false;                 // the forward kernel of layer l - 1 already summed its slabs into fsum[(l - 1) & 1]
     for (int l = 0; l < m->n_layers; ++l) {
         const dgprf_layer& y = m->layer[l];
         FwdArgs a;
@@ -376,17 +386,29 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
         int rc;
         if (w.L[l].tc_cols != 0 && dgprf_fwd_tc2_supported(a)) {                                                // pipelined
             if (l > 0 && a.Fprev.n_slabs > 1 && w.n_fsum > 0 && a.d <= 128) {      // (the WIDE variant's input split sums the slabs itself)
-                // every CTA of a row block reads the whole input tile: sum the partial slabs of F_{l-1} once (even two slabs:
-                // adding them in the CTA's own prologue costs a second dependent load round per CTA -- measured +50 us per
-                // layer at 65 536 rows against an 11 us launch)
-                rc = dgprf_launch_sum_slabs(a.Fprev, B, y.d_prev, wsf(ws, w.fsum), w.n_fsum, m->n_chains, st);
-                if (rc) return rc;
-                a.Fprev.ptr = wsf(ws, w.fsum); a.Fprev.cs = w.n_fsum; a.Fprev.ss = 0; a.Fprev.n_slabs = 1;
+                // every CTA of a row block reads the whole input tile: the partial slabs of F_{l-1} are summed once (even two
+                // slabs: adding them in the CTA's own prologue costs a second dependent load round per CTA -- measured +50 us
+                // per layer at 65 536 rows) -- by the tail of the previous layer's kernel when that was the pipelined one, by
+                // a launch otherwise
+                float* fs = wsf(ws, w.fsum) + (int64_t)((l - 1) & 1) * m->n_chains * w.n_fsum;
+                if (!fsum_ready) {
+                    rc = dgprf_launch_sum_slabs(a.Fprev, B, y.d_prev, fs, w.n_fsum, m->n_chains, st);
+                    if (rc) return rc;
+                }
+                a.Fprev.ptr = fs; a.Fprev.cs = w.n_fsum; a.Fprev.ss = 0; a.Fprev.n_slabs = 1;
+            }
+            fsum_ready = false;
+            if (fuse_sums && a.CS > 1 && l + 1 < m->n_layers && w.L[l + 1].tc2 && w.n_fsum > 0 && layer_d(m->layer[l + 1]) <= 128 &&
+                (int64_t)B * y.g <= w.n_fsum) {
+                a.Fsum = wsf(ws, w.fsum) + (int64_t)(l & 1) * m->n_chains * w.n_fsum; a.fsum_cs = w.n_fsum;
+                a.sum_ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.sumctr);
+                fsum_ready = true;
             }
             rc = dgprf_launch_fwd_tc2(a, m->n_chains, st);
         }
         else {
             DGPRF_REQUIRE(!a.phi_blocked, "layer %d: blocked saved features without the pipelined forward", l);
+            fsum_ready = false;
             rc = dgprf_launch_fwd_simt(a, m->n_chains, st);
         }
         if (rc) return rc;
@@ -462,6 +484,11 @@ extern "C" int dgprf_set_backward_hook(dgprf_layer_hook hook, void* user) {
 static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X, int64_t x_cs, int B, int mode,
                          void* ws, cudaStream_t st) {
     const int hyper = mode == DGPRF_MODE_HYPER;
+    // opt-in (DGPRF_FUSED_SLAB_SUMS=1), measured slower than the launches it removes: the ticket + sum are three to five DEPENDENT
+    // round trips at a CTA's tail (~1.8 us each under the other CTAs' streams), a PDL-overlapped k_sum_slabs launch is 7-17 us
+    // off the critical path of nothing (profiles/r02_fused_slab_sums.txt: configs[4] layer backward 523 -> 744 us, forward +8 us)
+    const bool fuse_sums = getenv("DGPRF_FUSED_SLAB_SUMS") != nullptr;
+    bool dsum_ready = false;                 // the backward kernel of layer l + 1 already summed its dF slabs into dfsum[(l + 1) & 1]
     for (int l = m->n_layers - 1; l >= 0; --l) {
         const dgprf_layer& y = m->layer[l];
         BwdArgs a;
@@ -491,15 +518,26 @@ static int backward_impl(const dgprf_model* m, const WsLayout& w, const float* X
         int rc;
         if (m->precision == DGPRF_PREC_TF32 && dgprf_bwd_tc2_supported(a)) {
             if (a.dF.n_slabs > 1) {
-                // every column-split CTA reads the whole dF tile: sum the partial slabs once instead of CS times
-                rc = dgprf_launch_sum_slabs(a.dF, B, y.g, wsf(ws, w.dfsum), w.n_dfsum, m->n_chains, st);
-                if (rc) return rc;
-                a.dF.ptr = wsf(ws, w.dfsum); a.dF.cs = w.n_dfsum; a.dF.ss = 0; a.dF.n_slabs = 1;
+                // every column-split CTA reads the whole dF tile: the partial slabs are summed once instead of CS times -- by
+                // the tail of the kernel of the layer above when that was the pipelined one, by a launch otherwise
+                float* ds = wsf(ws, w.dfsum) + (int64_t)((l + 1) & 1) * m->n_chains * w.n_dfsum;
+                if (!dsum_ready) {
+                    rc = dgprf_launch_sum_slabs(a.dF, B, y.g, ds, w.n_dfsum, m->n_chains, st);
+                    if (rc) return rc;
+                }
+                a.dF.ptr = ds; a.dF.cs = w.n_dfsum; a.dF.ss = 0; a.dF.n_slabs = 1;
+            }
+            dsum_ready = false;
+            if (fuse_sums && l > 0 && a.CS > 1 && w.L[l - 1].bwd2 && w.n_dfsum >= (int64_t)B * y.d_prev) {
+                a.Dsum = wsf(ws, w.dfsum) + (int64_t)(l & 1) * m->n_chains * w.n_dfsum; a.dsum_cs = w.n_dfsum;
+                a.sum_ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + w.sumctr) + (int64_t)m->n_chains * w.n_sumctr;
+                dsum_ready = true;
             }
             rc = dgprf_launch_bwd_tc2(a, m->n_chains, st);
         }
         else {
             DGPRF_REQUIRE(!a.phi_blocked, "layer %d: blocked saved features without the pipelined backward", l);
+            dsum_ready = false;
             rc = dgprf_launch_bwd_simt(a, m->n_chains, st);
         }
         if (rc) return rc;

@@ -126,6 +126,8 @@ struct FwdArgs {
     float* zt; int64_t zt_cs; float* wt; // pipelined TC forward: prepped z^T hi/lo [2][M][128] and W^T [NG][F] (workspace)
     float* at; float* ot;                // ... WIDE variant: input hi/lo [2][B][Kp] and Omega^T hi/lo [2][M][Kp]
     int32_t prepped;                     // zt / ot / wt were already written by k_prep_layers for this step
+    float* Fsum; int64_t fsum_cs;        // pipelined TC forward, CS > 1: dense [B][g] sum of the CS slabs, written by the last column
+    unsigned int* sum_ctr;               // split of a row block to finish (tickets [chains][row blocks], zero between launches); nullable
 };
 
 struct BwdArgs {
@@ -142,6 +144,8 @@ struct BwdArgs {
     float* Rpart;     int64_t r_cs;           // [CS][B]          R = rowsum(dP)     (hyper | mean)
     float* wp;                                // pipelined TC backward: zero-padded W rows [F][32] (workspace)
     int32_t prepped;                          // wp was already written by k_prep_layers for this step
+    float* Dsum; int64_t dsum_cs;             // pipelined TC backward, CS > 1: dense [B][d_prev] sum of the Dpart slabs, written by the last
+    unsigned int* sum_ctr;                    // column split of a row tile to finish (tickets [chains][row tiles], zero between launches); nullable
 };
 
 // ---- device helpers ----------------------------------------------------------------------

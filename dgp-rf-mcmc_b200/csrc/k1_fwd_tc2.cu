@@ -426,6 +426,48 @@ k1_fwd_tc2(const FwdArgs a, const int NS1, const int NSW_, long long* const tl, 
                 }
             }
         }
+        // ---- the LAST column split of a row block to get here adds the CS slabs of the block (slab order, the order of
+        //      k_sum_slabs: bit-identical) into the dense input of the next layer -- a ticket per (chain, row block) instead
+        //      of a ~7-10 us launch between two layers.  The ticket resets itself for the next launch. ----
+        if (a.do_gemm2 && a.Fsum != nullptr && warp < 4) {
+            uint32_t* last_s = reinterpret_cast<uint32_t*>(bars + 40);
+            asm volatile("bar.sync 2, 128;" ::: "memory");         // the slab rows of all four warps are written ...
+            if (tid == 0) {
+                __threadfence();                                   // ... and ordered before the ticket (fences are cumulative: one suffices)
+                unsigned int* ctr = a.sum_ctr + (int64_t)chain * gridDim.x + blockIdx.x;
+                const unsigned int old = atomicAdd(ctr, 1u);
+                const bool last = old + 1 == (unsigned int)a.CS;
+                if (last) atomicExch(ctr, 0u);
+                *last_s = last ? 1u : 0u;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (*last_s != 0u) {
+                __threadfence();
+                const int rows = min(V2_BM, a.B - row0);
+                const int64_t ss = (int64_t)a.B * a.g;
+                const float* src = a.Fpart + chain * a.fpart_cs + (int64_t)row0 * a.g;
+                float* dst = a.Fsum + chain * a.fsum_cs + (int64_t)row0 * a.g;
+                const int n = rows * a.g;
+                int e_lo = 0;
+                if (((ss | a.fpart_cs | a.fsum_cs) & 3) == 0 && (((int64_t)row0 * a.g) & 3) == 0) {      // 128-bit lanes
+                    const int nv = n >> 2;
+                    for (int e = tid; e < nv; e += 128) {
+                        float4 acc = __ldcg(reinterpret_cast<const float4*>(src) + e);
+                        for (int sl = 1; sl < a.CS; ++sl) {
+                            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + sl * ss) + e);
+                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        }
+                        reinterpret_cast<float4*>(dst)[e] = acc;
+                    }
+                    e_lo = nv << 2;
+                }
+                for (int e = e_lo + tid; e < n; e += 128) {
+                    float acc = __ldcg(src + e);
+                    for (int sl = 1; sl < a.CS; ++sl) acc += __ldcg(src + sl * ss + e);
+                    dst[e] = acc;
+                }
+            }
+        }
     } else if (warp == V2_EPI_WARPS) {
         // ===================================== MMA ISSUER =====================================
         // The whole warp walks the loop converged (waits included); one elected lane issues.  Descriptors are

@@ -451,6 +451,49 @@ k2_bwd_tc2(const BwdArgs a, const int pf_dist, long long* const tl, const __grid
                 }
                 tc::tc_fence_before();
                 asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");  // R_s and D3 are read: the next row tile may reuse them
+                if (a.Dsum != nullptr) {
+                    // the LAST column split of this row tile to get here adds the CS slabs of dU/dF_{l-1} (slab order, the order of
+                    // k_sum_slabs: bit-identical) into the dense dF the layer below reads -- a ticket per (chain, row tile)
+                    // instead of a ~9-17 us launch between two layers; the ticket resets itself for the next launch
+                    uint32_t* last_s = reinterpret_cast<uint32_t*>(bars + 16);
+                    const int rt = rs + rl * a.RS;
+                    if (tid == 0) {
+                        __threadfence();                 // the slab rows (written before the barrier above) are ordered before the ticket
+                        unsigned int* ctr = a.sum_ctr + (int64_t)chain * n_rt + rt;
+                        const unsigned int old = atomicAdd(ctr, 1u);
+                        const bool last = old + 1 == (unsigned int)(a.CS < n_ct ? a.CS : n_ct);
+                        if (last) atomicExch(ctr, 0u);
+                        *last_s = last ? 1u : 0u;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(B2_EPI_WARPS * 32) : "memory");
+                    if (*last_s != 0u) {
+                        __threadfence();
+                        const int rows = min(B2_BM, a.B - row0);
+                        const int64_t ss = (int64_t)a.B * a.d_prev;
+                        const float* src = a.Dpart + chain * a.d_cs + (int64_t)row0 * a.d_prev;
+                        float* dst = a.Dsum + chain * a.dsum_cs + (int64_t)row0 * a.d_prev;
+                        const int n = rows * a.d_prev;
+                        int e_lo = 0;
+                        if (((ss | a.d_cs | a.dsum_cs) & 3) == 0 && (((int64_t)row0 * a.d_prev) & 3) == 0) {      // 128-bit lanes
+                            const int nv = n >> 2;
+                            for (int e = tid; e < nv; e += ET) {
+                                float4 acc = __ldcg(reinterpret_cast<const float4*>(src) + e);
+                                for (int sl = 1; sl < a.CS; ++sl) {
+                                    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + sl * ss) + e);
+                                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                                }
+                                reinterpret_cast<float4*>(dst)[e] = acc;
+                            }
+                            e_lo = nv << 2;
+                        }
+                        for (int e = e_lo + tid; e < n; e += ET) {
+                            float acc = __ldcg(src + e);
+                            for (int sl = 1; sl < a.CS; ++sl) acc += __ldcg(src + sl * ss + e);
+                            dst[e] = acc;
+                        }
+                    }
+                    // (bars + 16 is rewritten only after the next row end's first bar.sync: every reader is past it by then)
+                }
                 if (k + 1 < T) {
                     // its dF tile may be staged once MMA-2(k), the last reader of the old one, is done
                     tc::mbar_wait((k & 1) ? barC1 : barC, (k >> 1) & 1);

@@ -103,6 +103,9 @@ const char* dgprf_last_error(void);
 int dgprf_version(void);
 
 /* ---- workspace ------------------------------------------------------------------------- */
+/* Bytes of scratch a call with (model, B, mode) needs.  The workspace must be ZERO-FILLED once when it is allocated (it
+ * holds the grid-barrier words of the fused step kernel and the tickets of the fused slab sums; every kernel leaves them
+ * at zero again) and must not be shared by calls running concurrently. */
 int dgprf_workspace_bytes(const dgprf_model* m, int B, int mode, size_t* bytes);
 
 /* ---- model-level hot path ---------------------------------------------------------------*/

@@ -217,3 +217,44 @@ def test_tc_hyper_gradients(name):
         model.grad_U(X, Y, N, full_bayesian=True)
         names = [nm for nm, _ in _ffi.profile_stop()]
         assert "k2_bwd_tc2" in names, names
+
+
+@pytest.mark.parametrize("shape", [
+    # (d_in, d_out, n_rf, n_gp, kinds, B, chains, full_bayesian)
+    (9, 1, [512, 512, 512], [9, 9, 1], ["RBF"] * 3, 1000, 1, False),          # configs[1] shape, ragged last row tile
+    (90, 1, [512, 512, 512], [30, 30, 1], ["RBF"] * 3, 1000, 4, False),       # configs[3] shape, chains batched per launch
+    (50, 5, [512, 768, 512], [12, 20, 5], ["ARC", "RBF", "ARC"], 4500, 1, False),   # many row tiles per CTA
+    (9, 1, [512, 512], [9, 1], ["RBF"] * 2, 777, 2, True),                    # hyper mode (T / R slabs next to dF)
+])
+def test_fused_slab_sums_equal_the_sum_launches_bit_for_bit(shape):
+    """The pipelined kernels add the column-split slabs of a row block in the tail of the LAST split to finish (a ticket per
+    row block) instead of a k_sum_slabs launch between two layers; same slab order, so the sampler state after several steps
+    must be bit-identical with and without DGPRF_FUSED_SLAB_SUMS=1 -- and the tickets must be back at zero after every launch.
+    (Opt-in: measured slower than the launches it removes, profiles/r02_fused_slab_sums.txt.)"""
+    d_in, d_out, n_rf, n_gp, kinds, B, chains, fb = shape
+    lik = "gaussian" if d_out == 1 else "softmax"
+    spec = ModelSpec.build(d_in, d_out, n_rf, n_gp, kinds, True, False, lik)
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(B, d_in, generator=g).cuda()
+    Y = (torch.randn(B, 1, generator=g) if lik == "gaussian" else torch.randint(0, d_out, (B, 1), generator=g).float()).cuda()
+    out = []
+    for no_fuse in (False, True):
+        if not no_fuse:
+            os.environ["DGPRF_FUSED_SLAB_SUMS"] = "1"
+        try:
+            torch.manual_seed(3)
+            e = Engine(spec, chains, precision=_ffi.PREC_TF32)
+            e.theta_w.normal_()
+            _ffi.profile_start()
+            for step in range(4):
+                e.step(X, Y, 5000.0, 1e-3, 0.9, 1.0, False, fb, 11, step)
+            names = [n for n, _ in _ffi.profile_stop()]
+            torch.cuda.synchronize()
+            out.append((e.theta_w.clone(), e.mom_w.clone(), e.theta_h.clone(), names))
+        finally:
+            os.environ.pop("DGPRF_FUSED_SLAB_SUMS", None)
+    (wa, ma, ha, na), (wb, mb, hb, nb) = out
+    assert torch.isfinite(wa).all()
+    assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(ha, hb)
+    assert any(n.startswith("k1_fwd_tc2") for n in na) and any(n.startswith("k2_bwd_tc2") for n in na)
+    assert na.count("k_sum_slabs") < nb.count("k_sum_slabs"), (na.count("k_sum_slabs"), nb.count("k_sum_slabs"))
