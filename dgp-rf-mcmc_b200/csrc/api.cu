@@ -344,7 +344,7 @@ static int forward_impl(const dgprf_model* m, const WsLayout& w, const float* X,
                 prepped = true;
             }
             if (mode >= DGPRF_MODE_TRAIN && s.bwd2) {
-                q.wp = wsf(ws, s.wp); q.n_wp = ceil_div(q.F * 32, 256);
+                q.wp = wsf(ws, s.wp); q.n_wp = ceil_div(q.F * 8, 256);
                 prepped = true;
             }
         }

@@ -76,11 +76,18 @@ __global__ void __launch_bounds__(256) k_prep_layers(const __grid_constant__ Pre
     }
     b -= y.n_wt;
     if (b < y.n_wp) {                                                 // ---- padded W rows ----
-        const int64_t i = (int64_t)b * 256 + threadIdx.x;
+        // four padded columns per thread, one 128-bit store (the buffer is 256-byte aligned, rows are 32 floats)
+        const int64_t i = ((int64_t)b * 256 + threadIdx.x) * 4;
         if (i >= (int64_t)y.F * 32) return;
         const int64_t f = i >> 5;
         const int j = (int)(i & 31);
-        y.wp[(int64_t)chain * y.F * 32 + i] = j < y.g ? tc::to_tf32(__ldg(y.W + chain * y.w_cs + f * y.g + j)) : 0.f;
+        const float* w = y.W + chain * y.w_cs + f * y.g;
+        float4 o;
+        o.x = j + 0 < y.g ? tc::to_tf32(__ldg(w + j + 0)) : 0.f;
+        o.y = j + 1 < y.g ? tc::to_tf32(__ldg(w + j + 1)) : 0.f;
+        o.z = j + 2 < y.g ? tc::to_tf32(__ldg(w + j + 2)) : 0.f;
+        o.w = j + 3 < y.g ? tc::to_tf32(__ldg(w + j + 3)) : 0.f;
+        *reinterpret_cast<float4*>(y.wp + (int64_t)chain * y.F * 32 + i) = o;
     }
 }
 
