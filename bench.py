@@ -357,11 +357,9 @@ def run_ours(args, rank, world):
     kw5 = dict(global_rows=c5["global_batch"], data_size=c5["N"], lr=c5["lr"], momentum_decay=c5["momentum_decay"], seed=3)
     n5 = max(5, min(K, 20))
     t5 = timed(lambda i: D.data_parallel_step(e5, X5l, Y5l, step=i, **kw5), n5, 3)
-    # the same step with ONE all-reduce of the whole flat buffer after the reverse pass (no overlap), for comparison
-    t5_plain = timed(lambda i: D.data_parallel_step(e5, X5l, Y5l, step=100 + i, overlap=False, **kw5), n5, 2) if dist is not None else t5
     flat5 = torch.zeros(e5.layout.w_len + 1, device=dev)
     t_ar = timed(lambda i: (dist.all_reduce(flat5) if dist is not None else None), 20, 3) / 20 if dist is not None else 0.0
-    t5, t_ar, t5_plain = max_over_ranks([t5, t_ar, t5_plain])
+    t5, t_ar = max_over_ranks([t5, t_ar])
     chk = e5.theta_w.double().sum().reshape(1)
     same = True
     if dist is not None:
@@ -372,10 +370,9 @@ def run_ours(args, rank, world):
     cfg5_out = {"config": c5, "n_gpus": world, "rows_per_gpu": int(X5l.shape[0]), "scaling": "strong",
                 "ms_per_step": 1e3 * t5 / n5, "value": n5 / t5, "unit": "it/s", "steps": n5,
                 "allreduce_us": 1e6 * t_ar, "allreduce_bytes": 4 * (e5.layout.w_len + 1),
-                "ms_per_step_single_all_reduce": 1e3 * t5_plain / n5,
-                "overlap": ("per-layer buckets: a layer's gradient slab sum + its NCCL all-reduce run on a side stream under the "
-                            "backward kernels of the layers below (dgprf_set_backward_hook); only layer 0's bucket is exposed"
-                            if dist is not None else "n/a (one GPU)"),
+                "reduction": ("one NCCL all-reduce of the flat [gW | sum ll] buffer after the reverse pass; per-layer buckets reduced "
+                              "under the reverse pass are implemented (overlap=True) and measured slower on NVSwitch: "
+                              "profiles/r02_dp_overlap_ab_{2,4,8}gpu.txt"),
                 "algorithmic_tflops": (sum(fwd5) + sum(bwd5)) / (t5 / n5) / 1e12,
                 "replicas_bit_identical": same, "finite": bool(torch.isfinite(e5.theta_w).all())}
     del e5, X5l, Y5l, flat5

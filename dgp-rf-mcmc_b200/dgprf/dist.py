@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 
-_DP_OVERLAP_DEFAULT = os.environ.get("DGPRF_DP_OVERLAP", "1") != "0"
+_DP_OVERLAP_DEFAULT = os.environ.get("DGPRF_DP_OVERLAP", "0") == "1"
 
 
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
@@ -82,6 +82,20 @@ def combine_predictive(lse_local: torch.Tensor, n_samples_local: int, aux_sum_lo
     return float(lp), aux
 
 
+def gradient_group(max_ctas: int = 16, ranks=None):
+    """A dedicated NCCL communicator for the gradient all-reduce of the data-parallel step, limited to `max_ctas` CTAs.
+    The pipelined backward kernels run one CTA per SM (227 KB of shared memory each); at the row counts of an 8-GPU split
+    they leave ~20 SMs free.  A collective that spreads over more SMs than that is not slower itself, but the NEXT backward
+    grid then cannot become resident at once and runs a second wave -- the overlapped reduction must stay inside the free
+    SMs.  Returns None (the default group) on backends without the option (gloo)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+
+
 class _OverlapState:
     """Side stream, per-layer events and bucket boundaries of the overlapped data-parallel step (one per engine)."""
 
@@ -111,11 +125,16 @@ def data_parallel_step(engine, X_local: torch.Tensor, Y_local: torch.Tensor, glo
     its replica with the same Philox (seed, step): the prior term theta/N is added inside the update, once, after the
     reduction; replicas stay bit-identical without a broadcast.  Returns sum_i ll_i [C].
 
-    overlap (default: on when world > 1; DGPRF_DP_OVERLAP=0 turns it off): the reverse pass retires the layers top-down, and
-    a layer's gradient slice is final as soon as its backward kernel has run -- so the slab sum of that slice and its
-    all-reduce are issued on a side stream from a per-layer host hook (dgprf_set_backward_hook) and run UNDER the backward
-    kernels of the layers below; only the bucket of layer 0 is exposed.  Every element is still reduced exactly once, by
-    the same collective, so the replicas stay bit-identical; overlap=False is one all-reduce of the whole buffer."""
+    overlap=True (opt-in; DGPRF_DP_OVERLAP=1 makes it the default for world > 1): the reverse pass retires the layers
+    top-down, and a layer's gradient slice is final as soon as its backward kernel has run -- so the slab sum of that slice and
+    its all-reduce are issued on a side stream from a per-layer host hook (dgprf_set_backward_hook) and run UNDER the backward
+    kernels of the layers below; only the bucket of layer 0 is exposed.  Every element is still reduced exactly once, so the
+    replicas stay bit-identical.  MEASURED on 2 / 4 / 8 B200s over NVSwitch (profiles/r02_dp_overlap_ab_{2,4,8}gpu.txt, A/B
+    inside one job): not faster -- the whole 4 MB all-reduce is 35-55 us of a 1-3 ms step and latency-bound, four 1 MB
+    all-reduces cost ~45 us each, their kernels slow the one-CTA-per-SM backward kernels they run beside, and the event
+    records between the backward kernels give up their programmatic launch overlap (8 GPUs: 0.965 ms with one all-reduce,
+    0.988 ms with per-layer buckets, 1.03-1.12 ms on communicators limited to 8 / 4 CTAs).  Hence opt-in; the default is ONE
+    all-reduce of the whole buffer after the reverse pass."""
     from . import _ffi
     w_len = engine.layout.w_len
     assert engine.C == 1, "the data-parallel step drives one replica per rank"

@@ -31,6 +31,15 @@ Y = torch.randn(B, 1, device=dev, generator=g)
 Xl, Yl = D.row_shard(X, Y, rank, world)
 Xl, Yl = Xl.contiguous(), Yl.contiguous()
 kw = dict(global_rows=B, data_size=N, lr=1e-4, momentum_decay=0.9, seed=3)
+# A/B switches of the gradient reduction: DP_OVERLAP=0|1 (default: the library's), DP_MIN_BUCKET=floats per bucket,
+# DP_MAX_CTAS=n: all-reduce on a dedicated NCCL communicator limited to n CTAs (so that its kernels fit on the SMs the
+# one-CTA-per-SM backward kernels leave free and never delay the residency of the next backward grid)
+if "DP_OVERLAP" in os.environ:
+    kw["overlap"] = os.environ["DP_OVERLAP"] == "1"
+if "DP_MIN_BUCKET" in os.environ:
+    kw["min_bucket_floats"] = int(os.environ["DP_MIN_BUCKET"])
+if world > 1 and "DP_MAX_CTAS" in os.environ:
+    kw["group"] = D.gradient_group(max_ctas=int(os.environ["DP_MAX_CTAS"]))
 for i in range(3):
     D.data_parallel_step(e, Xl, Yl, step=i, **kw)
 torch.cuda.synchronize()
@@ -59,6 +68,7 @@ if rank == 0:
     print(json.dumps({"workload": "configs[4] data-parallel step", "n_gpus": world, "precision": PREC, "global_batch": B,
                       "rows_per_gpu": Xl.shape[0], "ms_per_step": ms.item(), "it_per_s": 1e3 / ms.item(), "scaling": "strong",
                       "allreduce_bytes": 4 * (e.layout.w_len + 1), "replicas_bit_identical": same,
+                      "switches": {k: os.environ[k] for k in ("DP_OVERLAP", "DP_MIN_BUCKET", "DP_MAX_CTAS") if k in os.environ},
                       "finite": bool(torch.isfinite(e.theta_w).all())}))
 if world > 1:
     dist.barrier()
