@@ -96,6 +96,20 @@ def gradient_group(max_ctas: int = 16, ranks=None):
     return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
 
 
+def bucket_layers(off_W, w_len: int, min_bucket_floats: int):
+    """Layers whose hook closes a bucket of the overlapped reduction.  Buckets are contiguous runs [off_W[l], hi) of the flat
+    buffer [gW | sum ll] (w_len + 1 floats), built from the top layer down -- the order the reverse pass retires the layers:
+    a layer closes a bucket once the run holds min_bucket_floats, layer 0 closes the last one.  Returns the set of closing
+    layers; together the buckets tile [0, w_len + 1) exactly once."""
+    flush_at = set()
+    hi = w_len + 1
+    for l in range(len(off_W) - 1, -1, -1):
+        if l == 0 or hi - off_W[l] >= min_bucket_floats:
+            flush_at.add(l)
+            hi = off_W[l]
+    return flush_at
+
+
 class _OverlapState:
     """Side stream, per-layer events and bucket boundaries of the overlapped data-parallel step (one per engine)."""
 
@@ -103,14 +117,7 @@ class _OverlapState:
         lay = engine.layout
         self.comm = torch.cuda.Stream(device=engine.device)
         self.events = [torch.cuda.Event() for _ in lay.off_W]
-        # buckets are contiguous runs of the flat buffer, built from the top layer down (the order the reverse pass retires
-        # them): a layer closes a bucket once the run holds min_bucket_floats, layer 0 closes the last one
-        self.flush_at = set()
-        hi = lay.w_len + 1
-        for l in range(len(lay.off_W) - 1, -1, -1):
-            if l == 0 or hi - lay.off_W[l] >= min_bucket_floats:
-                self.flush_at.add(l)
-                hi = lay.off_W[l]
+        self.flush_at = bucket_layers(lay.off_W, lay.w_len, min_bucket_floats)
 
 
 def data_parallel_step(engine, X_local: torch.Tensor, Y_local: torch.Tensor, global_rows: int, data_size: float,

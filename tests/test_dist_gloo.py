@@ -67,6 +67,50 @@ def _worker_dp(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_buckets(rank, world, port, q):
+    """The bucketed reduction of the overlapped data-parallel step (dgprf/dist.py: bucket_layers): all-reducing the flat buffer
+    [gW | sum ll] bucket by bucket, top layer first, gives every rank the same buffer as one all-reduce of the whole of it."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.join(here, "..", "dgp-rf-mcmc_b200"), os.path.join(here, "..", "oracle")):
+        sys.path.insert(0, p)
+    import dgprf_oracle as O
+    from dgprf import dist as D
+    from dgprf.engine import FlatLayout, ModelSpec
+    _init(rank, world, port)
+    N, B = 1000, 41
+    n_rf, n_gp = [12, 8, 12], [3, 2, 1]
+    spec = ModelSpec.build(4, 1, n_rf, n_gp, ["RBF"] * 3, True, False, "gaussian")
+    lay = FlatLayout.of(spec)
+    p = O.init_params(4, 1, 3, n_rf, n_gp, None, True, "gaussian", seed=6)
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(B, 4, generator=g, dtype=torch.float64)
+    Y = torch.randn(B, 1, generator=g, dtype=torch.float64)
+    Xl, Yl = D.row_shard(X, Y, rank, world)
+    _, g_loc = O.grads_analytic(p, Xl, Yl, N, full_bayesian=False, hyper=False, allow_gradient_from_W=False)
+    flat = torch.zeros(lay.w_len + 1, dtype=torch.float64)
+    for l in range(3):
+        w = g_loc[f"W_{l}"].reshape(-1) * D.dp_scale(Xl.shape[0], B)
+        flat[lay.off_W[l]:lay.off_W[l] + w.numel()] = w
+    flat[lay.w_len] = O.log_likelihood(p, Xl, Yl).sum()
+    whole = flat.clone()
+    dist.all_reduce(whole)
+    ok = True
+    for min_bucket in (1, 40, 1 << 30):
+        closing = D.bucket_layers(lay.off_W, lay.w_len, min_bucket)
+        buf, hi, n_calls = flat.clone(), lay.w_len + 1, 0
+        for l in (2, 1, 0):                               # the order the reverse pass reports the layers
+            if l in closing:
+                dist.all_reduce(buf[lay.off_W[l]:hi])
+                hi = lay.off_W[l]
+                n_calls += 1
+        ok &= hi == 0 and n_calls == len(closing)
+        ok &= bool(torch.equal(buf, whole))               # two ranks: one addition per element, identical whatever the split
+    ok &= D.bucket_layers(lay.off_W, lay.w_len, 1) == {0, 1, 2} and D.bucket_layers(lay.off_W, lay.w_len, 1 << 30) == {0}
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
 def _worker_pred(rank, world, port, q):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -113,6 +157,10 @@ def test_shard_range_covers_everything():
 
 def test_data_parallel_gradient_allreduce_matches_single_process():
     _run(_worker_dp, 29611)
+
+
+def test_bucketed_gradient_reduction_matches_one_all_reduce():
+    _run(_worker_buckets, 29613)
 
 
 def test_sharded_predictive_average_matches_single_process():
