@@ -107,6 +107,7 @@ def _worker_buckets(rank, world, port, q):
         ok &= hi == 0 and n_calls == len(closing)
         ok &= bool(torch.equal(buf, whole))               # two ranks: one addition per element, identical whatever the split
     ok &= D.bucket_layers(lay.off_W, lay.w_len, 1) == {0, 1, 2} and D.bucket_layers(lay.off_W, lay.w_len, 1 << 30) == {0}
+    ok &= D.gradient_group(max_ctas=8) is None            # CTA-limited communicators are an NCCL option: default group on gloo
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
