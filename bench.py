@@ -359,7 +359,12 @@ def run_ours(args, rank, world):
     t5 = timed(lambda i: D.data_parallel_step(e5, X5l, Y5l, step=i, **kw5), n5, 3)
     flat5 = torch.zeros(e5.layout.w_len + 1, device=dev)
     t_ar = timed(lambda i: (dist.all_reduce(flat5) if dist is not None else None), 20, 3) / 20 if dist is not None else 0.0
-    t5, t_ar = max_over_ranks([t5, t_ar])
+    # the step's own reduction: the library's two-shot all-reduce over NVLink peer memory (csrc/k11_peer_allreduce.cu) when
+    # symmetric memory could be set up on every rank, else the NCCL all-reduce timed above
+    peer5 = getattr(e5, "_dp_peer", (None, None))[1]
+    t_peer = timed(lambda i: peer5(), 20, 3) / 20 if peer5 is not None else 0.0
+    peer_status = peer5.status() if peer5 is not None else None
+    t5, t_ar, t_peer = max_over_ranks([t5, t_ar, t_peer])
     chk = e5.theta_w.double().sum().reshape(1)
     same = True
     if dist is not None:
@@ -370,12 +375,16 @@ def run_ours(args, rank, world):
     cfg5_out = {"config": c5, "n_gpus": world, "rows_per_gpu": int(X5l.shape[0]), "scaling": "strong",
                 "ms_per_step": 1e3 * t5 / n5, "value": n5 / t5, "unit": "it/s", "steps": n5,
                 "allreduce_us": 1e6 * t_ar, "allreduce_bytes": 4 * (e5.layout.w_len + 1),
-                "reduction": ("one NCCL all-reduce of the flat [gW | sum ll] buffer after the reverse pass; per-layer buckets reduced "
-                              "under the reverse pass are implemented (overlap=True) and measured slower on NVSwitch: "
-                              "profiles/r02_dp_overlap_ab_{2,4,8}gpu.txt"),
+                "peer_allreduce_us": 1e6 * t_peer if peer5 is not None else None, "peer_status": peer_status,
+                "reduction": ("n/a (one GPU)" if dist is None else
+                              "peer: two-shot all-reduce over NVLink peer memory by the library's own kernels (k11_signal_wait / "
+                              "k11_reduce_push: every rank sums its 1/world slice of all ranks' gradients in rank order and pushes "
+                              "the result to every rank); allreduce_us is NCCL's all-reduce of the same buffer, for comparison"
+                              if peer5 is not None else
+                              "nccl: one all-reduce of the flat [gW | sum ll] buffer (symmetric memory unavailable on this box)"),
                 "algorithmic_tflops": (sum(fwd5) + sum(bwd5)) / (t5 / n5) / 1e12,
                 "replicas_bit_identical": same, "finite": bool(torch.isfinite(e5.theta_w).all())}
-    del e5, X5l, Y5l, flat5
+    del e5, X5l, Y5l, flat5, peer5
     torch.cuda.empty_cache()
 
     # ---- the collective part ends here: the other ranks leave, rank 0 finishes its single-GPU measurements ----

@@ -63,6 +63,8 @@ SIGNATURES = {
     "dgprf_grad_finalize": (_I, [_MP, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP]),
     "dgprf_grad_finalize_layer": (_I, [_MP, _I, _I, _I, _VP, _SZ, _VP, _I64, _F, _VP]),
     "dgprf_set_backward_hook": (_I, [_VP, _VP]),
+    "dgprf_peer_allreduce": (_I, [_VP, _VP, _I, _I, _I64, C.c_uint32, C.c_uint32, _VP]),
+    "dgprf_peer_allreduce_status": (_I, [C.POINTER(C.c_uint32)]),
     "dgprf_gradients": (_I, [_MP, _VP, _I64, _VP, _I64, _I, _I, _VP, _SZ, _VP, _I64, _VP, _I64, _F, _I, _VP, _F, _I, _VP]),
     "dgprf_sgmcmc_update": (_I, [_VP, _VP, _I64, _I64, _I, _VP, _I64, _I, _I64, _SP, _I,
                                  _F, _F, _F, _F, _I, _U64, _U64, _VP, _VP, _VP]),

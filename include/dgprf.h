@@ -156,6 +156,18 @@ int dgprf_grad_finalize_layer(const dgprf_model* m, int layer, int B, int mode, 
 typedef void (*dgprf_layer_hook)(int layer, void* user);
 int dgprf_set_backward_hook(dgprf_layer_hook hook, void* user);
 
+/* Two-shot all-reduce (sum) of the flat gradient of the data-parallel split over NVLink peer memory (csrc/k11_peer_allreduce.cu),
+ * the library-free alternative to one NCCL all-reduce per step.  The 1/B mean of models/dgp.py:174 over a minibatch whose rows
+ * are split over GPUs is the sum of the per-GPU data terms; every replica then applies the update of models/dgp.py:206-216.
+ *   bufs[r]: rank r's symmetric allocation [2][n_pad] floats, mapped on every rank (half 0: r's own gradient, half 1: receives
+ *            the reduced gradient); sigs[r]: rank r's zero-initialised signal pad (uint32 words; 2*world words are used from
+ *            sig_word_offset on).  n_pad % (4*world) == 0.  epoch: 1, 2, 3, ... -- the same on every rank for the same step.
+ * Collective: every rank of the group calls it once per step on its own stream; nothing blocks the host.  A rank whose peers
+ * never arrive gives up after ~2 s and raises the sticky word dgprf_peer_allreduce_status returns (0 = healthy). */
+int dgprf_peer_allreduce(void* const* bufs, void* const* sigs, int rank, int world, int64_t n_pad,
+                         unsigned int epoch, unsigned int sig_word_offset, void* stream);
+int dgprf_peer_allreduce_status(unsigned int* status);
+
 /* The whole gradient pass behind tf.GradientTape in one call (models/dgp.py:186-204 of sgmcmc_update, :246-251 of
  * precond_update, experiments/utils_training.py:341-354 of the M-step):
  *   dgprf_forward(mode) + dgprf_loglik(inv_B) + dgprf_backward + dgprf_grad_finalize.

@@ -33,6 +33,9 @@ for n in (4, 8, 16):
     groups[n] = D.gradient_group(max_ctas=n)
 VARIANTS = [  # (name, overlap, max_ctas, min_bucket_floats)
     ("one all-reduce after the reverse pass", False, 0, 65536),
+    ("PEER two-shot all-reduce over NVLink peer memory (k11)", "peer", 0, 65536),
+    ("one all-reduce after the reverse pass (again)", False, 0, 65536),
+    ("PEER two-shot all-reduce (again)", "peer", 0, 65536),
     ("one all-reduce, 16 CTAs", False, 16, 65536),
     ("per-layer buckets under the reverse pass", True, 0, 65536),
     ("per-layer buckets, 16 CTAs", True, 16, 65536),
@@ -41,10 +44,15 @@ VARIANTS = [  # (name, overlap, max_ctas, min_bucket_floats)
     ("two buckets [L4 L3 L2 | L1 L0], 8 CTAs", True, 8, 600000),
     ("one bucket issued from the hook of layer 0, 8 CTAs", True, 8, 1 << 30),
 ]
+if os.environ.get("DP_AB_ONLY"):                      # e.g. DP_AB_ONLY="one all-reduce after,PEER": substring filter
+    keys = os.environ["DP_AB_ONLY"].split(",")
+    VARIANTS = [v for v in VARIANTS if any(k in v[0] for k in keys)]
 STEPS = 20
 step = 0
 for name, ov, ctas, mb in VARIANTS:
     kw = dict(base, overlap=ov, min_bucket_floats=mb, group=groups[ctas])
+    if ov == "peer":
+        kw = dict(base, reduction="peer")
     res = []
     for rep in range(3):
         for i in range(3):
