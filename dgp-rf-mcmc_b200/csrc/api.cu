@@ -651,8 +651,15 @@ extern "C" int dgprf_gradients(const dgprf_model* m, const float* X, int64_t x_c
     }
     if (gW) {
         DGPRF_REQUIRE(gw_cs >= w.w_len, "gW chain stride %lld < %lld", (long long)gw_cs, (long long)w.w_len);
-        rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), w.n_gwpart, w.w_len, n_part, m->w_base, m->w_cs, prior_inv_N, gW, gw_cs,
-                                        w.w_len, m->n_chains, st);
+        if (prior_inv_N == 0.f) {
+            // no prior term (the data-parallel step adds theta / N once, in the update): the plain slab sum, 128-bit lanes with
+            // four slabs in flight per thread (same slab order as k_grad_finalize; 19 -> ~11 us for 18 slabs of 4 MB)
+            SlabMat s;
+            s.ptr = wsf(ws, w.gwpart); s.cs = w.n_gwpart; s.ss = w.w_len; s.ld = 1; s.n_slabs = n_part;
+            rc = dgprf_launch_sum_slabs(s, (int)w.w_len, 1, gW, gw_cs, m->n_chains, st);
+        } else
+            rc = dgprf_launch_grad_finalize(wsf(ws, w.gwpart), w.n_gwpart, w.w_len, n_part, m->w_base, m->w_cs, prior_inv_N, gW, gw_cs,
+                                            w.w_len, m->n_chains, st);
         if (rc) return rc;
     }
     if (gH) {

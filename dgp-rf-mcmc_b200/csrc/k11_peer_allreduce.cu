@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) k11_reduce_push(const __grid_constant__ P
         for (int r = 0; r < kMaxPeers; ++r)
             if (r < a.world) st_peer_v4(a.buf[r] + a.n_pad + off, acc);
     }
-    __threadfence_system();
+    // no fence here: the phase-1 signal is raised by the NEXT kernel of the stream, after a system-scope fence of its own, and a
+    // kernel boundary orders this grid's stores before it (a fence.sys per thread made the 2-GPU case 30 -> 49 us)
 }
 
 extern "C" int dgprf_peer_allreduce(void* const* bufs, void* const* sigs, int rank, int world, int64_t n_pad,
@@ -111,7 +112,7 @@ extern "C" int dgprf_peer_allreduce(void* const* bufs, void* const* sigs, int ra
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t slice4 = n_pad / world / 4;
     int blocks = ceil_div(slice4, 256);
-    if (blocks > 8 * 148) blocks = 8 * 148;          // a peer load is a ~2-3 us round trip: one or two vectors per thread, all in flight
+    if (blocks > 4 * 148) blocks = 4 * 148;          // a peer load is a ~2-3 us round trip: a few vectors per thread, all peers in flight
     { ProfScope _ps("k11_signal_wait", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k11_signal_wait, dim3(1), dim3(32), 0, st, a, 0)); }
     { ProfScope _ps("k11_reduce_push", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k11_reduce_push, dim3(blocks), dim3(256), 0, st, a)); }
     { ProfScope _ps("k11_signal_wait", st); DGPRF_CHECK_CUDA(dgprf_launch_pdl(k11_signal_wait, dim3(1), dim3(32), 0, st, a, 1)); }

@@ -14,7 +14,7 @@ __global__ void k_sum_slabs(SlabMat m, int B, int ncol, float* out, int64_t out_
 }
 
 // dense rows (ld == ncol): a slab is one contiguous array, so no index arithmetic and 128-bit accesses when aligned;
-// slabs are added in slab order (the order of slab_load), four loads in flight per thread
+// slabs are added in slab order (the order of slab_load), four to eight loads in flight per thread
 template <typename T>
 __global__ void __launch_bounds__(256) k_sum_slabs_dense(const float* __restrict__ base, int64_t cs, int64_t ss, int n_slabs, int64_t n,
                                                          float* __restrict__ out, int64_t out_cs) {
@@ -25,6 +25,16 @@ __global__ void __launch_bounds__(256) k_sum_slabs_dense(const float* __restrict
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         T acc = __ldg(p + e);
         int sl = 1;
+        for (; sl + 7 < n_slabs; sl += 8) {            // many slabs (gW: one per row split): eight loads in flight, adds in slab order
+            T t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldg(p + (sl + u) * sst + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if constexpr (sizeof(T) == 16) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+                else acc += t[u];
+            }
+        }
         for (; sl + 3 < n_slabs; sl += 4) {
             const T t0 = __ldg(p + sl * sst + e), t1 = __ldg(p + (sl + 1) * sst + e), t2 = __ldg(p + (sl + 2) * sst + e),
                     t3 = __ldg(p + (sl + 3) * sst + e);
