@@ -17,7 +17,7 @@
 // peer has finished reading it; a peer pushes into half 1 only after phase 0 of the next step, which this rank signals
 // after its update kernel has consumed half 1 (stream order).
 // A wait gives up after ~2 s of polling (a peer that died must not hang the GPU): it raises the sticky error word the
-// host reads back with dgprf_peer_allreduce_status.
+// host reads back (and clears) with dgprf_peer_allreduce_status.
 // ~4 MB at 8 GPUs: 0.5 MB slices, 7 peer reads + 7 peer writes of 0.5 MB per rank: the cost is three launch latencies and
 // two signal round trips, not bandwidth (NCCL's ring / NVLS all-reduce of the same buffer: 35-55 us).
 #include "kernels.cuh"
@@ -122,6 +122,10 @@ extern "C" int dgprf_peer_allreduce(void* const* bufs, void* const* sigs, int ra
 
 extern "C" int dgprf_peer_allreduce_status(unsigned int* status) {
     DGPRF_REQUIRE(status != nullptr, "status is NULL");
-    DGPRF_CHECK_CUDA(cudaMemcpyFromSymbol(status, g_k11_error, sizeof(unsigned int)));
+    DGPRF_CHECK_CUDA(cudaMemcpyFromSymbol(status, g_k11_error, sizeof(unsigned int)));      // (synchronises the device)
+    if (*status != 0) {                                // read and clear: the word reports the waits since the last query
+        const unsigned int zero = 0;
+        DGPRF_CHECK_CUDA(cudaMemcpyToSymbol(g_k11_error, &zero, sizeof(unsigned int)));
+    }
     return DGPRF_OK;
 }

@@ -163,7 +163,8 @@ int dgprf_set_backward_hook(dgprf_layer_hook hook, void* user);
  *            the reduced gradient); sigs[r]: rank r's zero-initialised signal pad (uint32 words; 2*world words are used from
  *            sig_word_offset on).  n_pad % (4*world) == 0.  epoch: 1, 2, 3, ... -- the same on every rank for the same step.
  * Collective: every rank of the group calls it once per step on its own stream; nothing blocks the host.  A rank whose peers
- * never arrive gives up after ~2 s and raises the sticky word dgprf_peer_allreduce_status returns (0 = healthy). */
+ * never arrive gives up after ~2 s and raises the sticky word dgprf_peer_allreduce_status returns and clears (0 = healthy;
+ * else (phase + 1) << 8 | peer of a wait that timed out).  The status call synchronises the device. */
 int dgprf_peer_allreduce(void* const* bufs, void* const* sigs, int rank, int world, int64_t n_pad,
                          unsigned int epoch, unsigned int sig_word_offset, void* stream);
 int dgprf_peer_allreduce_status(unsigned int* status);

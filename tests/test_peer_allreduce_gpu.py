@@ -1,0 +1,112 @@
+"""K11 (csrc/k11_peer_allreduce.cu): the two-shot all-reduce protocol of the data-parallel step, exercised on ONE GPU.
+
+The C entry point only sees raw pointers -- one buffer [2][n_pad] and one signal pad per rank -- so `world` ranks can be played
+by `world` CUDA streams of one process: every "rank" launches its three kernels on its own stream, the signal kernels of all
+ranks are co-resident (one warp each) and hand-shake through the pads exactly as they do across NVLink.  (The real thing,
+8 processes over NVSwitch against NCCL: scripts/peer_allreduce_check.py -> profiles/r02_peer_allreduce_check.txt.)
+The reduced half must equal the sum taken in rank order, bit for bit, on every rank, epoch after epoch; no wait may time out."""
+import ctypes as C
+
+import pytest
+import torch
+
+from dgprf import _ffi
+
+pytestmark = pytest.mark.gpu
+SIG_WORD = 256
+
+
+def _run(world, n, epochs, streams=None):
+    q = 4 * world
+    n_pad = (n + q - 1) // q * q
+    dev = torch.device("cuda")
+    bufs = [torch.zeros(2 * n_pad, device=dev) for _ in range(world)]
+    sigs = [torch.zeros(1024, dtype=torch.int32, device=dev) for _ in range(world)]
+    streams = streams or [torch.cuda.Stream() for _ in range(world)]
+    B = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    S = (C.c_void_p * world)(*[s.data_ptr() for s in sigs])
+    L = _ffi.lib()
+    g = torch.Generator(device=dev).manual_seed(17 * world + n)
+    for epoch in epochs:
+        xs = [torch.randn(n, device=dev, generator=g) * (10.0 ** (r % 3 - 1)) for r in range(world)]
+        for r in range(world):
+            bufs[r][:n].copy_(xs[r])
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                _ffi.check(L.dgprf_peer_allreduce(B, S, r, world, n_pad, epoch, SIG_WORD, _ffi.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = xs[0].clone()
+        for r in range(1, world):
+            ref += xs[r]                                  # rank order, one fp32 addition per rank: what every owner computes
+        for r in range(world):
+            assert torch.equal(bufs[r][n_pad:n_pad + n], ref), (world, n, epoch, r)
+            assert torch.equal(bufs[r][:n], xs[r])        # the gradient half is only ever read
+            pad = sigs[r][SIG_WORD:SIG_WORD + 2 * world].cpu().view(torch.int32)
+            assert bool((pad == (epoch if epoch < 2 ** 31 else epoch - 2 ** 32)).all()), pad
+    st = C.c_uint32(1)
+    _ffi.check(L.dgprf_peer_allreduce_status(C.byref(st)))
+    assert st.value == 0, f"a signal wait timed out: phase {(st.value >> 8) - 1}, peer {st.value & 255}"
+
+
+def test_one_rank_is_a_copy():
+    _run(1, 5, epochs=(1, 2, 3))
+
+
+# up to four emulated ranks: with eight, one rank's signal kernel still ended up queued behind another rank's spinning one on
+# the test box (time-out reported, data correct) -- eight REAL ranks are scripts/peer_allreduce_check.py's job
+CASES = [(2, 33), (3, 1000), (4, 4097)]
+
+
+def test_ranks_on_streams_reduce_to_the_rank_order_sum():
+    """Every emulated rank needs its signal kernel co-resident with the others': with more streams than hardware work queues
+    (8 by default, and a long-lived pytest process has created many streams already) one rank's kernel can sit BEHIND another
+    rank's spinning one -- a false dependency the 2 s time-out would report.  So the emulation runs in a fresh process with
+    CUDA_DEVICE_MAX_CONNECTIONS=32: one queue per rank."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path[:0] = [%r, %r]; import test_peer_allreduce_gpu as t\n"
+            "t._run(1, 8, epochs=(1,))   # loads both kernels: a first-use (lazy) module load behind a spinning kernel of ANOTHER emulated rank would wait for it\n"
+            "for w, n in t.CASES:\n    t._run(w, n, epochs=(1, 2, 3)); print('PEER-OK', w, n, flush=True)\n"
+            "t.epochs_may_skip_and_wrap(); print('PEER-OK wrap')"
+            % (here, os.path.join(here, "..", "dgp-rf-mcmc_b200")))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("PEER-OK") == len(CASES) + 1, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def epochs_may_skip_and_wrap():
+    """Signals compare as monotonic epochs (signed difference): gaps are fine, and so is the wrap of the 32-bit counter."""
+    q = 8
+    dev = torch.device("cuda")
+    world, n = 2, 64
+    bufs = [torch.zeros(2 * 64, device=dev) for _ in range(world)]
+    sigs = [torch.zeros(1024, dtype=torch.int32, device=dev) for _ in range(world)]
+    B = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    S = (C.c_void_p * world)(*[s.data_ptr() for s in sigs])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    L = _ffi.lib()
+    for epoch in (5, 2 ** 31 - 1, 2 ** 31 + 3, 2 ** 32 - 1, 2):       # 2 follows 2^32 - 1: wrapped
+        for r in range(world):
+            bufs[r][:n].fill_(float(r + 1) + (epoch % 7))
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                _ffi.check(L.dgprf_peer_allreduce(B, S, r, world, 64, epoch, SIG_WORD, _ffi.stream_ptr()))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert float(bufs[r][64]) == 3.0 + 2 * (epoch % 7)
+    st = C.c_uint32(1)
+    _ffi.check(L.dgprf_peer_allreduce_status(C.byref(st)))
+    assert st.value == 0
+
+
+def test_argument_validation():
+    L = _ffi.lib()
+    one = (C.c_void_p * 1)(0x1000)
+    assert L.dgprf_peer_allreduce(one, one, 0, 1, 6, 1, SIG_WORD, None) != 0 and b"multiple" in L.dgprf_last_error()
+    assert L.dgprf_peer_allreduce(one, one, 0, 1, 8, 0, SIG_WORD, None) != 0 and b"epoch" in L.dgprf_last_error()
+    assert L.dgprf_peer_allreduce(one, one, 1, 1, 8, 1, SIG_WORD, None) != 0 and b"rank" in L.dgprf_last_error()
+    assert L.dgprf_peer_allreduce(one, one, 0, 17, 68, 1, SIG_WORD, None) != 0 and b"world" in L.dgprf_last_error()
