@@ -108,6 +108,14 @@ def _worker_buckets(rank, world, port, q):
         ok &= bool(torch.equal(buf, whole))               # two ranks: one addition per element, identical whatever the split
     ok &= D.bucket_layers(lay.off_W, lay.w_len, 1) == {0, 1, 2} and D.bucket_layers(lay.off_W, lay.w_len, 1 << 30) == {0}
     ok &= D.gradient_group(max_ctas=8) is None            # CTA-limited communicators are an NCCL option: default group on gloo
+    # the peer-memory all-reduce needs CUDA symmetric memory: where a rank cannot set it up, EVERY rank agrees on the library
+    # collective (None), and an explicit reduction="peer" raises instead of splitting the ranks between two protocols
+    ok &= D._make_peer(64, torch.device("cpu"), None, required=False) is None
+    try:
+        D._make_peer(64, torch.device("cpu"), None, required=True)
+        ok = False
+    except RuntimeError as exc:
+        ok &= "not available on every rank" in str(exc)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
